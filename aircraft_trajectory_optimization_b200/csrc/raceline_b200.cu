@@ -1,0 +1,386 @@
+// libraceline_b200: C ABI + kernel dispatch (see include/raceline_b200.h).
+//
+// Replaces, for the raceline NLP, what CasADi's nlpsol derives from the SX graph the reference
+// builds (drone3d/raceline/base_raceline.py:752-799) and evaluates on every IPOPT iteration
+// (:160-165): nlp_f, nlp_g, nlp_grad_f, nlp_jac_g, nlp_hess_l.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/raceline_b200.h"
+#include "common.cuh"
+#include "generated/pf_drone_quat_global.cuh"
+#include "generated/pf_drone_quat_param_gr.cuh"
+#include "generated/pf_drone_ypr_global.cuh"
+#include "generated/pf_drone_ypr_param_gr.cuh"
+#include "generated/pf_point_pm_global.cuh"
+#include "generated/pf_point_pm_param_gr.cuh"
+#include "rk4_cells.cuh"
+#include "colloc_cells.cuh"
+#include "simple_rows.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(const std::string& m) {
+  g_err = m;
+  return 1;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return 1;
+}
+#define CK(call)                                        \
+  do {                                                  \
+    cudaError_t e__ = (call);                           \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+struct VariantInfo {
+  const char* name;
+  int nz, nu, nvp;
+};
+const VariantInfo kVariants[] = {
+    {"drone_quat_global", PF_drone_quat_global::NZ, PF_drone_quat_global::NU, PF_drone_quat_global::NVP},
+    {"drone_quat_param_gr", PF_drone_quat_param_gr::NZ, PF_drone_quat_param_gr::NU, PF_drone_quat_param_gr::NVP},
+    {"point_pm_global", PF_point_pm_global::NZ, PF_point_pm_global::NU, PF_point_pm_global::NVP},
+    {"point_pm_param_gr", PF_point_pm_param_gr::NZ, PF_point_pm_param_gr::NU, PF_point_pm_param_gr::NVP},
+    {"drone_ypr_param_gr", PF_drone_ypr_param_gr::NZ, PF_drone_ypr_param_gr::NU, PF_drone_ypr_param_gr::NVP},
+    {"drone_ypr_global", PF_drone_ypr_global::NZ, PF_drone_ypr_global::NU, PF_drone_ypr_global::NVP},
+};
+constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
+
+template <class PF>
+cudaError_t launch_cells_t(const RbDev& d, const RbBatch& b, cudaStream_t st) {
+  const long long cells = (long long)b.B * d.N;
+  if (d.transcription == RB_RK4) {
+    constexpr int CPB = RB_CELL_THREADS / (PF::NX + 1);
+    const long long blocks = (cells + CPB - 1) / CPB;
+    rk4_cells_kernel<PF><<<(unsigned)blocks, RB_CELL_THREADS, 0, st>>>(d, b);
+  } else {
+    const long long blocks = (cells + RB_COLLOC_CPB - 1) / RB_COLLOC_CPB;
+    colloc_cells_kernel<PF><<<(unsigned)blocks, RB_COLLOC_CPB * 8, 0, st>>>(d, b);
+  }
+  g_launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_cells(int variant, const RbDev& d, const RbBatch& b, cudaStream_t st) {
+  switch (variant) {
+    case 0: return launch_cells_t<PF_drone_quat_global>(d, b, st);
+    case 1: return launch_cells_t<PF_drone_quat_param_gr>(d, b, st);
+    case 2: return launch_cells_t<PF_point_pm_global>(d, b, st);
+    case 3: return launch_cells_t<PF_point_pm_param_gr>(d, b, st);
+    case 4: return launch_cells_t<PF_drone_ypr_param_gr>(d, b, st);
+    case 5: return launch_cells_t<PF_drone_ypr_global>(d, b, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+struct Workspace {
+  int B = 0;
+  double *x = nullptr, *lam_g = nullptr, *lam_f = nullptr, *vp = nullptr;
+  double *f = nullptr, *grad_f = nullptr, *g = nullptr, *jac = nullptr, *hess = nullptr;
+  void* scratch = nullptr;
+  cudaStream_t stream = nullptr;
+};
+
+}  // namespace
+
+struct rb_problem {
+  RbDev d{};
+  int variant = -1;
+  int nz = 0, nu = 0, nvp = 0;
+  std::vector<void*> owned;  // device allocations
+  std::vector<long long> jac_sp, hess_sp;
+  Workspace ws;
+  std::mutex mu;
+};
+
+namespace {
+
+template <class T>
+int upload(rb_problem* p, const T* src, size_t n, const T** dst) {
+  *dst = nullptr;
+  if (!src || n == 0) return 0;
+  void* dev = nullptr;
+  CK(cudaMalloc(&dev, n * sizeof(T)));
+  p->owned.push_back(dev);
+  CK(cudaMemcpy(dev, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  *dst = static_cast<const T*>(dev);
+  return 0;
+}
+
+void free_ws(Workspace& w) {
+  for (double* q : {w.x, w.lam_g, w.lam_f, w.vp, w.f, w.grad_f, w.g, w.jac, w.hess})
+    if (q) cudaFree(q);
+  if (w.scratch) cudaFree(w.scratch);
+  w = Workspace{.stream = w.stream};
+}
+
+int ensure_ws(rb_problem* p, int B) {
+  Workspace& w = p->ws;
+  if (!w.stream) CK(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+  if (w.B >= B) return 0;
+  cudaStream_t st = w.stream;
+  free_ws(w);
+  w.stream = st;
+  const RbDev& d = p->d;
+  auto alloc = [&](double** q, size_t n) -> cudaError_t { return cudaMalloc((void**)q, n * sizeof(double)); };
+  CK(alloc(&w.x, (size_t)B * d.nw));
+  CK(alloc(&w.lam_g, (size_t)B * (d.ng > 0 ? d.ng : 1)));
+  CK(alloc(&w.lam_f, (size_t)B));
+  CK(alloc(&w.vp, (size_t)B * p->nvp));
+  CK(alloc(&w.f, (size_t)B));
+  CK(alloc(&w.grad_f, (size_t)B * d.nw));
+  CK(alloc(&w.g, (size_t)B * (d.ng > 0 ? d.ng : 1)));
+  CK(alloc(&w.jac, (size_t)B * (d.nnzj > 0 ? d.nnzj : 1)));
+  CK(alloc(&w.hess, (size_t)B * (d.nnzh > 0 ? d.nnzh : 1)));
+  CK(cudaMalloc(&w.scratch, rb_eval_scratch_bytes(p, B)));
+  w.B = B;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rb_last_error(void) { return g_err.c_str(); }
+
+int rb_device_count(int* count) {
+  CK(cudaGetDeviceCount(count));
+  return 0;
+}
+
+int rb_set_device(int device) {
+  CK(cudaSetDevice(device));
+  return 0;
+}
+
+long long rb_launch_count(void) { return g_launches.load(); }
+
+int rb_problem_create(const rb_problem_desc* s, rb_problem** out) {
+  if (!s || !out) return fail("rb_problem_create: null argument");
+  *out = nullptr;
+  int variant = -1;
+  for (int i = 0; i < kNumVariants; ++i)
+    if (s->variant && std::strcmp(s->variant, kVariants[i].name) == 0) variant = i;
+  if (variant < 0) return fail(std::string("model variant not compiled into libraceline_b200: ") + (s->variant ? s->variant : "(null)"));
+  if (s->transcription != RB_RK4 && s->transcription != RB_COLLOC) return fail("unknown transcription");
+  if (s->transcription == RB_COLLOC && s->K != 7) return fail("collocation kernels are built for K = 7");
+  auto* p = new rb_problem();
+  p->variant = variant;
+  p->nz = kVariants[variant].nz;
+  p->nu = kVariants[variant].nu;
+  p->nvp = kVariants[variant].nvp;
+  RbDev& d = p->d;
+  d.transcription = s->transcription;
+  d.N = s->N;
+  d.K = s->K;
+  d.nw = s->nw;
+  d.ng = s->ng;
+  d.nnzj = s->nnz_jac;
+  d.nnzh = s->nnz_hess;
+  d.cell_nj = s->cell_nj;
+  d.cell_nh = s->cell_nh;
+  d.cell_ncp = s->cell_ncp;
+  d.n_srow = s->n_srow;
+  d.n_shess = s->n_shess;
+  const int P = s->K + 1;
+  const int S = p->nz + 2 * p->nu;
+  if (s->nw != s->N + s->N * P * S) {
+    delete p;
+    return fail("nw does not match N + N*(K+1)*(nz+2nu)");
+  }
+  const size_t ncr = s->transcription == RB_RK4 ? (size_t)(p->nz + p->nu) : (size_t)s->cell_nj;  // colloc: see structure.py
+  int rc = 0;
+  rc |= upload(p, s->R, (size_t)p->nu, &d.R);
+  rc |= upload(p, s->dR, (size_t)p->nu, &d.dR);
+  rc |= upload(p, s->fc, (size_t)s->N * P * 13, &d.fc);
+  const size_t nrow_tab = s->transcription == RB_RK4 ? (size_t)s->N * (p->nz + p->nu) : (size_t)s->N * RB_COLLOC_NCR(p->nz, p->nu);
+  (void)ncr;
+  rc |= upload(p, s->cell_row, nrow_tab, &d.cell_row);
+  rc |= upload(p, s->cell_coef, nrow_tab, &d.cell_coef);
+  rc |= upload(p, s->cell_partner, nrow_tab, &d.cell_partner);
+  rc |= upload(p, s->cell_pcoef, nrow_tab, &d.cell_pcoef);
+  rc |= upload(p, s->cell_off, nrow_tab, &d.cell_off);
+  rc |= upload(p, s->cell_par, (size_t)s->N * s->cell_ncp, &d.cell_par);
+  rc |= upload(p, s->cell_jslot, (size_t)s->N * s->cell_nj, &d.cell_jslot);
+  rc |= upload(p, s->cell_hslot, (size_t)s->N * s->cell_nh, &d.cell_hslot);
+  if (s->n_srow > 0) {
+    rc |= upload(p, s->srow_row, (size_t)s->n_srow, &d.srow_row);
+    rc |= upload(p, s->srow_kind, (size_t)s->n_srow, &d.srow_kind);
+    rc |= upload(p, s->srow_scale, (size_t)s->n_srow, &d.srow_scale);
+    rc |= upload(p, s->srow_var_ptr, (size_t)s->n_srow + 1, &d.srow_var_ptr);
+    rc |= upload(p, s->srow_form_ptr, (size_t)s->n_srow + 1, &d.srow_form_ptr);
+    rc |= upload(p, s->srow_coef_ptr, (size_t)s->n_srow + 1, &d.srow_coef_ptr);
+    const size_t nvar = (size_t)s->srow_var_ptr[s->n_srow];
+    rc |= upload(p, s->srow_var, nvar, &d.srow_var);
+    rc |= upload(p, s->srow_jslot, nvar, &d.srow_jslot);
+    rc |= upload(p, s->srow_A, (size_t)s->srow_coef_ptr[s->n_srow], &d.srow_A);
+    rc |= upload(p, s->srow_c, (size_t)s->srow_form_ptr[s->n_srow], &d.srow_c);
+  }
+  if (s->n_shess > 0) {
+    rc |= upload(p, s->shess_slot, (size_t)s->n_shess, &d.shess_slot);
+    rc |= upload(p, s->shess_add, (size_t)s->n_shess, &d.shess_add);
+    rc |= upload(p, s->shess_ptr, (size_t)s->n_shess + 1, &d.shess_ptr);
+    const size_t ne = (size_t)s->shess_ptr[s->n_shess];
+    rc |= upload(p, s->shess_row, ne, &d.shess_row);
+    rc |= upload(p, s->shess_coef, ne, &d.shess_coef);
+    rc |= upload(p, s->shess_scale, ne, &d.shess_scale);
+  }
+  if (rc) {
+    rb_problem_destroy(p);
+    return 1;
+  }
+  auto pack = [&](std::vector<long long>& v, int nrow, int ncol, const int64_t* colind, const int64_t* row, int nnz) {
+    v.clear();
+    v.push_back(nrow);
+    v.push_back(ncol);
+    for (int i = 0; i <= ncol; ++i) v.push_back(colind ? colind[i] : 0);
+    for (int i = 0; i < nnz; ++i) v.push_back(row ? row[i] : 0);
+  };
+  pack(p->jac_sp, s->ng, s->nw, s->jac_colind, s->jac_row, s->nnz_jac);
+  pack(p->hess_sp, s->nw, s->nw, s->hess_colind, s->hess_row, s->nnz_hess);
+  *out = p;
+  return 0;
+}
+
+void rb_problem_destroy(rb_problem* p) {
+  if (!p) return;
+  for (void* q : p->owned) cudaFree(q);
+  cudaStream_t st = p->ws.stream;
+  free_ws(p->ws);
+  if (st) cudaStreamDestroy(st);
+  delete p;
+}
+
+int rb_problem_nvp(const rb_problem* p) { return p ? p->nvp : 0; }
+
+int rb_sparsity_size(const rb_problem* p, int which, size_t* n) {
+  if (!p || !n) return fail("rb_sparsity_size: null argument");
+  *n = which == 0 ? p->jac_sp.size() : p->hess_sp.size();
+  return 0;
+}
+
+int rb_sparsity_get(const rb_problem* p, int which, long long* out) {
+  if (!p || !out) return fail("rb_sparsity_get: null argument");
+  const auto& v = which == 0 ? p->jac_sp : p->hess_sp;
+  std::memcpy(out, v.data(), v.size() * sizeof(long long));
+  return 0;
+}
+
+size_t rb_eval_scratch_bytes(const rb_problem* p, int B) {
+  if (!p || B <= 0) return 0;
+  return (size_t)B * p->d.N * sizeof(double) + 256;
+}
+
+int rb_eval_batch(const rb_problem* p, int B, const double* x, const double* lam_g, const double* lam_f,
+                  const double* vp, int vp_stride, const double* fc_b, double* f, double* grad_f,
+                  double* g, double* jac, double* hess, void* scratch, void* stream) {
+  if (!p || !x || !vp) return fail("rb_eval_batch: null problem / x / vp");
+  if (B <= 0) return 0;
+  if (hess && !lam_g && p->d.ng > 0) return fail("rb_eval_batch: hess requested without lam_g");
+  if (f && !scratch) return fail("rb_eval_batch: f requested without scratch");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  RbBatch b{};
+  b.B = B;
+  b.x = x;
+  b.lam_g = lam_g;
+  b.lam_f = lam_f;
+  b.vp = vp;
+  b.vp_stride = vp_stride;
+  b.fc_b = fc_b;
+  b.f = f;
+  b.grad_f = grad_f;
+  b.g = g;
+  b.jac = jac;
+  b.hess = hess;
+  b.fpart = f ? static_cast<double*>(scratch) : nullptr;
+  const RbDev& d = p->d;
+  CK(launch_cells(p->variant, d, b, st));
+  if (d.n_srow > 0 && (g || jac)) {
+    const long long t = (long long)B * d.n_srow;
+    simple_rows_kernel<<<(unsigned)((t + 127) / 128), 128, 0, st>>>(d, b);
+    g_launches++;
+    CK(cudaGetLastError());
+  }
+  if (d.n_shess > 0 && hess) {
+    const long long t = (long long)B * d.n_shess;
+    simple_hess_kernel<<<(unsigned)((t + 127) / 128), 128, 0, st>>>(d, b);
+    g_launches++;
+    CK(cudaGetLastError());
+  }
+  if (f) {
+    objective_sum_kernel<<<(unsigned)(((long long)B * 32 + 127) / 128), 128, 0, st>>>(d, b, d.N);
+    g_launches++;
+    CK(cudaGetLastError());
+  }
+  return 0;
+}
+
+// ---- host-buffer entry points -------------------------------------------------------------------
+static int host_eval(const rb_problem* cp, int B, const double* x, const double* vp, const double* lam_f,
+                     const double* lam_g, double* f, double* grad_f, double* g, double* jac, double* hess) {
+  if (!cp || !x || !vp) return fail("null problem / x / vp");
+  if (B <= 0) return 0;
+  rb_problem* p = const_cast<rb_problem*>(cp);
+  std::lock_guard<std::mutex> lock(p->mu);
+  if (ensure_ws(p, B)) return 1;
+  Workspace& w = p->ws;
+  const RbDev& d = p->d;
+  cudaStream_t st = w.stream;
+  CK(cudaMemcpyAsync(w.x, x, (size_t)B * d.nw * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(w.vp, vp, (size_t)B * p->nvp * sizeof(double), cudaMemcpyHostToDevice, st));
+  const double* dl = nullptr;
+  const double* dlf = nullptr;
+  if (hess) {
+    if (!lam_g && d.ng > 0) return fail("nlp_hess_l needs lam_g");
+    if (d.ng > 0) CK(cudaMemcpyAsync(w.lam_g, lam_g, (size_t)B * d.ng * sizeof(double), cudaMemcpyHostToDevice, st));
+    dl = w.lam_g;
+    if (lam_f) {
+      CK(cudaMemcpyAsync(w.lam_f, lam_f, (size_t)B * sizeof(double), cudaMemcpyHostToDevice, st));
+      dlf = w.lam_f;
+    }
+  }
+  if (rb_eval_batch(p, B, w.x, dl, dlf, w.vp, p->nvp, nullptr, f ? w.f : nullptr, grad_f ? w.grad_f : nullptr,
+                    g ? w.g : nullptr, jac ? w.jac : nullptr, hess ? w.hess : nullptr, w.scratch, st))
+    return 1;
+  if (f) CK(cudaMemcpyAsync(f, w.f, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (grad_f) CK(cudaMemcpyAsync(grad_f, w.grad_f, (size_t)B * d.nw * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (g) CK(cudaMemcpyAsync(g, w.g, (size_t)B * d.ng * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (jac) CK(cudaMemcpyAsync(jac, w.jac, (size_t)B * d.nnzj * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (hess) CK(cudaMemcpyAsync(hess, w.hess, (size_t)B * d.nnzh * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int rb_nlp_f(const rb_problem* p, int B, const double* x, const double* vp, double* f) {
+  return host_eval(p, B, x, vp, nullptr, nullptr, f, nullptr, nullptr, nullptr, nullptr);
+}
+int rb_nlp_g(const rb_problem* p, int B, const double* x, const double* vp, double* g) {
+  return host_eval(p, B, x, vp, nullptr, nullptr, nullptr, nullptr, g, nullptr, nullptr);
+}
+int rb_nlp_grad_f(const rb_problem* p, int B, const double* x, const double* vp, double* f, double* grad_f) {
+  return host_eval(p, B, x, vp, nullptr, nullptr, f, grad_f, nullptr, nullptr, nullptr);
+}
+int rb_nlp_jac_g(const rb_problem* p, int B, const double* x, const double* vp, double* g, double* jac) {
+  return host_eval(p, B, x, vp, nullptr, nullptr, nullptr, nullptr, g, jac, nullptr);
+}
+int rb_nlp_hess_l(const rb_problem* p, int B, const double* x, const double* vp, const double* lam_f,
+                  const double* lam_g, double* hess) {
+  return host_eval(p, B, x, vp, lam_f, lam_g, nullptr, nullptr, nullptr, nullptr, hess);
+}
+int rb_nlp_eval_all(const rb_problem* p, int B, const double* x, const double* vp, const double* lam_f,
+                    const double* lam_g, double* f, double* grad_f, double* g, double* jac, double* hess) {
+  return host_eval(p, B, x, vp, lam_f, lam_g, f, grad_f, g, jac, hess);
+}
+
+}  // extern "C"

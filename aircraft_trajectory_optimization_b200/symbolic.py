@@ -309,10 +309,12 @@ class Graph:
                     adj[y] = add(adj[y], t) if y in adj else t
         return adj
 
-    def forward_sparse(self, outputs, wrt, nodes=None):
+    def forward_sparse(self, outputs, wrt, nodes=None, seeds=None):
         '''
         forward-mode sweep carrying a sparse gradient {column: node id} per node.
-        wrt: {INPUT node id: column}.  Returns a list of dicts, one per output.
+        wrt: {INPUT node id: column}.  seeds: optional {INPUT node id: seed node id} (default 1);
+        mapping several inputs to one column with symbolic seeds gives a directional derivative.
+        Returns a list of dicts, one per output.
         '''
         if nodes is None:
             nodes = self.reachable(outputs)
@@ -328,7 +330,7 @@ class Graph:
             if o == INPUT:
                 c = wrt.get(n)
                 if c is not None:
-                    D[n] = {c: one}
+                    D[n] = {c: one if seeds is None else seeds.get(n, one)}
                 continue
             x = a[n]
             dx = D.get(x, empty)

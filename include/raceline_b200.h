@@ -1,0 +1,136 @@
+/*
+ * raceline_b200.h -- C ABI of libraceline_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the hot path of thomasfork/aircraft_trajectory_optimization: the five NLP
+ * functions CasADi creates when the reference calls
+ *     self.solver = ca.nlpsol('solver', 'ipopt', prob, opts)      drone3d/raceline/base_raceline.py:799
+ * and that IPOPT calls on every iteration of
+ *     sol = self.solver(x0=..., lbx=..., ubx=..., lbg=..., ubg=...)   drone3d/raceline/base_raceline.py:160-165
+ * i.e. nlp_f, nlp_g, nlp_grad_f, nlp_jac_g, nlp_hess_l, plus batched device-pointer variants and
+ * the block-structured KKT solve used by the batched interior-point driver.
+ *
+ * A *problem* (rb_problem) is the structured description of one raceline NLP that the Python
+ * builders produce in place of the reference's SX graph (same decision-vector layout and g row
+ * order: base_raceline.py:232-239, :670-717).  All index tables are int32,
+ * all values fp64.  Plain pointers and sizes only; no exceptions cross this boundary.
+ *
+ * Return value: 0 on success, non-zero on failure (CasADi convention); rb_last_error() describes
+ * the last failure on the calling thread.  NaN/Inf in outputs are not errors.
+ */
+#ifndef RACELINE_B200_H
+#define RACELINE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rb_problem rb_problem; /* opaque, owns device copies of the tables below */
+
+/* transcription kinds */
+#define RB_RK4 0     /* direct multiple shooting, classic RK4 (base_raceline.py:363-391, :1052-1112) */
+#define RB_COLLOC 1  /* direct orthogonal collocation, Legendre K points (base_raceline.py:398-490) */
+
+/* Host-side description of a problem.  Arrays are copied; the caller may free them after
+ * rb_problem_create returns.  Sections that do not apply are passed as NULL / 0. */
+typedef struct rb_problem_desc {
+  int transcription;      /* RB_RK4 | RB_COLLOC */
+  const char* variant;    /* generated model variant, e.g. "drone_quat_param_gr" */
+  int N, K;               /* intervals, collocation order (K = 0 for RK4) */
+  int nw, ng, nnz_jac, nnz_hess;
+  const double* R;        /* [nu] diagonal of the input cost            (base_raceline.py:616-623) */
+  const double* dR;       /* [nu] diagonal of the input-rate cost */
+  const double* fc;       /* [N*(K+1)][13] frame constants Rp|ks|ky|kn||xcs| (NULL: global frame) */
+
+  /* ---- interval cells: rows produced by the dynamics of interval n ---------------------- */
+  const int32_t* cell_row;       /* rk4: [N][nz+nu] g row of out_c / input row j (-1: none)
+                                    colloc: [N][ncr] see aircraft_trajectory_optimization_b200/structure.py */
+  const double* cell_coef;       /* same shape: sign / coefficient applied to the cell output */
+  const int32_t* cell_partner;   /* same shape: index in w of the linear partner variable (-1: none) */
+  const double* cell_pcoef;      /* same shape: coefficient of the partner variable */
+  const double* cell_off;        /* same shape: constant offset of the row */
+  const double* cell_par;        /* [N][ncp] per-cell scalars (rk4: du_coef; colloc: unused) */
+  const int32_t* cell_jslot;     /* flattened local-Jacobian-slot -> CCS position (-1: not stored) */
+  const int32_t* cell_hslot;     /* flattened local-Hessian-slot  -> CCS position (-1: not stored) */
+  int cell_nj, cell_nh;          /* local slots per cell in the two tables */
+  int cell_ncp;
+
+  /* ---- simple rows: g = scale * sum_m (sum_i A[m][i] w[idx_i] + c[m])^(1 or 2) ------------- */
+  int n_srow;
+  const int32_t* srow_row;       /* [n_srow] g row */
+  const int32_t* srow_kind;      /* [n_srow] 0 affine (one form), 1 sum of squares */
+  const int32_t* srow_scale;     /* [n_srow] -1: scale 1; k >= 0: scale = 1 / vp[k]^2 */
+  const int32_t* srow_var_ptr;   /* [n_srow+1] into srow_var / srow_jslot */
+  const int32_t* srow_var;       /* w indices */
+  const int32_t* srow_jslot;     /* CCS position of (row, var) */
+  const int32_t* srow_form_ptr;  /* [n_srow+1] into srow_c; coefficient block of form m of row r starts at
+                                    srow_coef_ptr[r] + (m - srow_form_ptr[r]) * nvar_r */
+  const int32_t* srow_coef_ptr;  /* [n_srow+1] into srow_A */
+  const double* srow_A;
+  const double* srow_c;
+
+  /* ---- Hessian contributions of the simple rows (constant * lam_g[row] * scale) ----------- */
+  int n_shess;
+  const int32_t* shess_slot;     /* [n_shess] CCS position in hess_l */
+  const int32_t* shess_add;      /* [n_shess] 1: add to what the cell kernel wrote, 0: assign */
+  const int32_t* shess_ptr;      /* [n_shess+1] into the three arrays below */
+  const int32_t* shess_row;
+  const double* shess_coef;
+  const int32_t* shess_scale;
+
+  /* ---- CCS patterns (returned by the sparsity queries; CasADi layout) ---------------------- */
+  const int64_t* jac_colind;     /* [nw+1] */
+  const int64_t* jac_row;        /* [nnz_jac] */
+  const int64_t* hess_colind;    /* [nw+1] */
+  const int64_t* hess_row;       /* [nnz_hess] upper triangle */
+} rb_problem_desc;
+
+const char* rb_last_error(void);
+int rb_device_count(int* count);
+int rb_set_device(int device);
+
+int rb_problem_create(const rb_problem_desc* desc, rb_problem** out);
+void rb_problem_destroy(rb_problem* p);
+int rb_problem_nvp(const rb_problem* p); /* vehicle parameters per problem instance */
+
+/* CasADi compressed sparsity of jac_g / hess_l: [nrow, ncol, colind[ncol+1], row[nnz]] as long long.
+ * Replaces Function::sparsity_out of nlp_jac_g / nlp_hess_l [CasADi, third party]. */
+int rb_sparsity_size(const rb_problem* p, int which /*0 jac_g, 1 hess_l*/, size_t* n_entries);
+int rb_sparsity_get(const rb_problem* p, int which, long long* out);
+
+/* ---- batched evaluation on DEVICE pointers (asynchronous on `stream`) ------------------------
+ * One *eval* = f, grad_f, g, jac_g values, hess_l values of one problem instance at (x, lam_g, lam_f).
+ *   x      [B][nw]        lam_g [B][ng]      lam_f [B]       vp [B or 1][nvp] (vp_stride 0: shared)
+ *   fc_b   optional per-instance frame constants [B][N*(K+1)][13] (NULL: the problem's own)
+ * outputs (any may be NULL = not wanted):
+ *   f [B]   grad_f [B][nw]   g [B][ng]   jac [B][nnz_jac]   hess [B][nnz_hess]
+ * scratch: device buffer of rb_eval_scratch_bytes(p, B) bytes.
+ * `stream` is a cudaStream_t passed as void*. */
+size_t rb_eval_scratch_bytes(const rb_problem* p, int B);
+int rb_eval_batch(const rb_problem* p, int B, const double* x, const double* lam_g, const double* lam_f,
+                  const double* vp, int vp_stride, const double* fc_b, double* f, double* grad_f,
+                  double* g, double* jac, double* hess, void* scratch, void* stream);
+
+/* ---- CasADi-shaped HOST entry points (synchronous; copies in and out) ------------------------
+ * Same argument meaning as CasADi's nlp_* oracle functions [third party]; p (parameters) is the
+ * vehicle-parameter vector.  Any output pointer may be NULL.  B instances at once (B = 1 is the
+ * reference's call pattern). */
+int rb_nlp_f(const rb_problem* p, int B, const double* x, const double* vp, double* f);
+int rb_nlp_g(const rb_problem* p, int B, const double* x, const double* vp, double* g);
+int rb_nlp_grad_f(const rb_problem* p, int B, const double* x, const double* vp, double* f, double* grad_f);
+int rb_nlp_jac_g(const rb_problem* p, int B, const double* x, const double* vp, double* g, double* jac);
+int rb_nlp_hess_l(const rb_problem* p, int B, const double* x, const double* vp, const double* lam_f,
+                  const double* lam_g, double* hess);
+/* everything in one pass: the bench's "jac_g + hess_lag eval" through host buffers */
+int rb_nlp_eval_all(const rb_problem* p, int B, const double* x, const double* vp, const double* lam_f,
+                    const double* lam_g, double* f, double* grad_f, double* g, double* jac, double* hess);
+
+/* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
+long long rb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RACELINE_B200_H */
