@@ -1,0 +1,133 @@
+'''
+The BASELINE.json problem instances, built twice: by the product builders and by
+the oracle's literal restatement of the reference.  Waypoints are the ones in the reference's
+scripts (scripts/fig_8.py:10-12, scripts/race.py:12-14, scripts/obstacles.py:14-16).
+'''
+from types import SimpleNamespace as NS
+
+import numpy as np
+
+from aircraft_trajectory_optimization_b200.pytypes import DroneConfig, PointConfig
+from aircraft_trajectory_optimization_b200.centerlines import SplineCenterlineConfig, GateShape, \
+    SplineCenterline
+from aircraft_trajectory_optimization_b200 import raceline as RL
+
+TRACKS = {
+    'fig8': (np.array([[0, 5, 0, -5, 0, 5, 0, -5], [0, 1, 2, 1, 0, -1, -2, -1],
+                       [10, 5, 0, -5, -10, -5, 0, 5]], dtype=float), GateShape.CIRCLE),
+    'race': (np.array([[-1.1, 9.2, 9.2, -4.5, -4.5, 4.75, -2.8], [-1.6, 6.6, -4, -6, -6, -0.9, 6.8],
+                       [3.6, 1.0, 1.2, 3.5, 0.8, 1.2, 1.2]]), GateShape.SQUARE),
+    'obs': (np.array([[-5, -2.75, -0.66, 2.95, 8.67, 9.2, 1.57, -2.39, -4.7, -2.39, 4.23, -2.66],
+                      [4.5, -0.08, -1.36, 1.25, 6.69, -3.6, -6.43, -6, -6.43, -6.23, -0.66, 6.66],
+                      [1.2, 2.815, 3.9, 2.815, 1.0, 1.0, 2.815, 3.9, 2.815, 1.0, 1.0, 1.0]]), GateShape.CIRCLE),
+}
+
+
+def make_line(track, cls=SplineCenterline):
+    x, shape = TRACKS[track]
+    cfg = SplineCenterlineConfig(x=x.copy())
+    cfg.closed = True
+    cfg.gate_shape = shape
+    line = cls(cfg)
+    if track == 'obs':
+        line.config.gate_s = None        # scripts/obstacles.py:22-23
+    return line
+
+
+def synthetic_tube_arrays(s):
+    ''' stand-in tube while trimesh is unavailable '''
+    s = np.asarray(s, dtype=float)
+    ball_p = np.stack([s, 0.3 * np.sin(2 * np.pi * s / 12), 0.2 * np.cos(2 * np.pi * s / 12)], axis=1)
+    return ball_p, 0.9 * np.ones(len(s))
+
+
+# name -> (track, frame, vehicle, rk4, N full, N small, quat, tube)
+CASES = {
+    'fig8_global_colloc_drone': ('fig8', 'global', 'drone', False, 50, 8, True, False),      # C1
+    'fig8_global_colloc_point': ('fig8', 'global', 'point', False, 50, 8, True, False),      # WS of C1
+    'fig8_param_colloc_drone': ('fig8', 'parametric', 'drone', False, 50, 8, True, False),
+    'fig8_param_colloc_drone_euler': ('fig8', 'parametric', 'drone', False, 50, 8, False, False),
+    'fig8_param_colloc_point': ('fig8', 'parametric', 'point', False, 50, 8, True, False),
+    'race_global_rk4_drone': ('race', 'global', 'drone', True, 70, 7, True, False),
+    'race_global_rk4_point': ('race', 'global', 'point', True, 70, 7, True, False),
+    'race_param_rk4_drone': ('race', 'parametric', 'drone', True, 70, 7, True, False),       # C2 / C5
+    'race_param_rk4_point': ('race', 'parametric', 'point', True, 70, 7, True, False),       # WS of C2
+    'race_param_rk4_drone_euler': ('race', 'parametric', 'drone', True, 70, 7, False, False),
+    'obs_param_colloc_drone': ('obs', 'parametric', 'drone', False, 100, 12, True, True),    # C3
+    'obs_param_colloc_point': ('obs', 'parametric', 'point', False, 100, 12, True, True),    # WS of C3
+}
+
+
+def vehicle_config(vehicle, quat=True, tube=False, **kw):
+    rc = dict(collision_radius=0.4) if tube else {}
+    if vehicle == 'drone':
+        return DroneConfig(global_r=True, use_quat=quat, **rc, **kw)
+    return PointConfig(global_r=True, **rc, **kw)
+
+
+def build_product(name, small=False, N=None, vehicle_kw=None):
+    track, frame, vehicle, rk4, n_full, n_small, quat, tube = CASES[name]
+    N = N or (n_small if small else n_full)
+    line = make_line(track)
+    vc = vehicle_config(vehicle, quat, tube, **(vehicle_kw or {}))
+    if frame == 'global':
+        cfg = RL.GlobalRacelineConfig(N=N, use_rk4=rk4, closed=True, verbose=False,
+                                      gate_xi=line.config.x[0], gate_xj=line.config.x[1],
+                                      gate_xk=line.config.x[2])
+        cls = RL.GlobalDroneRaceline if vehicle == 'drone' else RL.GlobalPointRaceline
+        args = (line, cfg, vc)
+    else:
+        cfg = RL.ParametricRacelineConfig(N=N, use_rk4=rk4, closed=True, verbose=False)
+        if track != 'obs':
+            cfg.fixed_gates = line.config.s[:-1]          # drone3d/utils/solve_util.py:56-57
+        if tube:
+            K = 7
+            tau = RL.get_collocation_coefficients(K)[0]
+            ds = (line.s_max() - line.s_min()) / N
+            s_all = np.array([line.s_min() + ds * (n + tau[k]) for n in range(N) for k in range(K + 1)])
+            bp, br = synthetic_tube_arrays(s_all)
+            t = RL.ObstacleFreeTube(bp, br, vc.collision_radius)
+            cls = RL.ParametricObstacleDroneRaceline if vehicle == 'drone' else RL.ParametricObstaclePointRaceline
+            args = (line, cfg, vc, None, t)
+        else:
+            cls = RL.ParametricDroneRaceline if vehicle == 'drone' else RL.ParametricPointRaceline
+            args = (line, cfg, vc)
+    if vehicle == 'drone':
+        return cls(*args, generate_ws=False)
+    return cls(*args)
+
+
+def build_oracle(name, small=False, N=None, vehicle_kw=None):
+    from oracle.ref_centerline import RefSplineCenterline
+    from oracle.ref_raceline import RefRaceline, RefTube
+    track, frame, vehicle, rk4, n_full, n_small, quat, tube = CASES[name]
+    N = N or (n_small if small else n_full)
+    line = make_line(track, RefSplineCenterline)
+    vc = vehicle_config(vehicle, quat, tube, **(vehicle_kw or {}))
+    cfg = NS(N=N, K=7, use_rk4=rk4, R=1e-7, dR=1e-7, h0=1, v0=1, closed=True, fix_gate_center=False)
+    rt = None
+    if frame == 'global':
+        cfg.gate_xi, cfg.gate_xj, cfg.gate_xk = line.config.x
+    else:
+        cfg.fixed_gates = line.config.s[:-1] if track != 'obs' else None
+        cfg.force_regularity = True
+        if tube:
+            from oracle.ref_discretization import get_collocation_coefficients
+            tau = get_collocation_coefficients(7)[0]
+            ds = (line.s_max() - line.s_min()) / N
+            s_all = np.array([line.s_min() + ds * (n + tau[k]) for n in range(N) for k in range(8)])
+            bp, br = synthetic_tube_arrays(s_all)
+            rt = RefTube(bp, br, vc.collision_radius)
+    return RefRaceline(line, cfg, vc, frame, vehicle, tube=rt)
+
+
+def build_case(name, small=False, N=None, vehicle_kw=None):
+    return build_product(name, small, N, vehicle_kw), build_oracle(name, small, N, vehicle_kw)
+
+
+def eval_point(st, seed):
+    ''' SURVEY.md s8d eval-point distribution '''
+    rng = np.random.default_rng(seed)
+    x = np.clip(st.w0 + 1e-2 * rng.standard_normal(st.nw), st.lbw, st.ubw)
+    lam = rng.standard_normal(st.ng)
+    return x, lam
