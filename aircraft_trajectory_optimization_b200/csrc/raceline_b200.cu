@@ -29,6 +29,14 @@ namespace {
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 
+// optional instrumentation: CUDA-event pairs around the interval-cell kernel (the dominant one)
+struct CellTimer {
+  bool on = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+  size_t used = 0;
+} g_timer;
+std::mutex g_timer_mu;
+
 int fail(const std::string& m) {
   g_err = m;
   return 1;
@@ -305,7 +313,22 @@ int rb_eval_batch(const rb_problem* p, int B, const double* x, const double* lam
   b.hess = hess;
   b.fpart = f ? static_cast<double*>(scratch) : nullptr;
   const RbDev& d = p->d;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (g_timer.on) {
+    std::lock_guard<std::mutex> lock(g_timer_mu);
+    if (g_timer.used == g_timer.ev.size()) {
+      cudaEvent_t a, c;
+      CK(cudaEventCreate(&a));
+      CK(cudaEventCreate(&c));
+      g_timer.ev.emplace_back(a, c);
+    }
+    ev0 = g_timer.ev[g_timer.used].first;
+    ev1 = g_timer.ev[g_timer.used].second;
+    g_timer.used++;
+    CK(cudaEventRecord(ev0, st));
+  }
   CK(launch_cells(p->variant, d, b, st));
+  if (ev1) CK(cudaEventRecord(ev1, st));
   if (d.n_srow > 0 && (g || jac)) {
     const long long t = (long long)B * d.n_srow;
     simple_rows_kernel<<<(unsigned)((t + 127) / 128), 128, 0, st>>>(d, b);
@@ -323,6 +346,69 @@ int rb_eval_batch(const rb_problem* p, int B, const double* x, const double* lam
     g_launches++;
     CK(cudaGetLastError());
   }
+  return 0;
+}
+
+int rb_profile_enable(int on) {
+  std::lock_guard<std::mutex> lock(g_timer_mu);
+  g_timer.on = on != 0;
+  g_timer.used = 0;
+  return 0;
+}
+
+int rb_profile_cell_ms(double* total_ms, int* launches) {
+  std::lock_guard<std::mutex> lock(g_timer_mu);
+  double tot = 0.0;
+  for (size_t i = 0; i < g_timer.used; ++i) {
+    CK(cudaEventSynchronize(g_timer.ev[i].second));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, g_timer.ev[i].first, g_timer.ev[i].second));
+    tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = (int)g_timer.used;
+  g_timer.used = 0;
+  return 0;
+}
+
+// FP64 FMA throughput of this device (the denominator for the compute-bound shooting kernel)
+__global__ void fp64_peak_kernel(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+int rb_fp64_peak(double* tflops) {
+  int dev = 0, sms = 0;
+  CK(cudaGetDevice(&dev));
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int blocks = sms * 8, threads = 256, iters = 1 << 16;
+  double* buf = nullptr;
+  CK(cudaMalloc(&buf, sizeof(double) * blocks * threads));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  fp64_peak_kernel<<<blocks, threads>>>(buf, 1024);
+  double best = 0.0;
+  for (int rep = 0; rep < 3; ++rep) {
+    CK(cudaEventRecord(e0));
+    fp64_peak_kernel<<<blocks, threads>>>(buf, iters);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double fl = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+    if (fl > best) best = fl;
+  }
+  g_launches += 4;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  if (tflops) *tflops = best;
   return 0;
 }
 

@@ -46,7 +46,7 @@ class _Desc(ctypes.Structure):
 EXPORTS = ['rb_last_error', 'rb_device_count', 'rb_set_device', 'rb_problem_create', 'rb_problem_destroy',
            'rb_problem_nvp', 'rb_sparsity_size', 'rb_sparsity_get', 'rb_eval_scratch_bytes', 'rb_eval_batch',
            'rb_nlp_f', 'rb_nlp_g', 'rb_nlp_grad_f', 'rb_nlp_jac_g', 'rb_nlp_hess_l', 'rb_nlp_eval_all',
-           'rb_launch_count']
+           'rb_launch_count', 'rb_profile_enable', 'rb_profile_cell_ms', 'rb_fp64_peak']
 
 
 def load_library():
@@ -78,6 +78,9 @@ def load_library():
     lib.rb_nlp_hess_l.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp]
     lib.rb_nlp_eval_all.argtypes = [vp, ctypes.c_int] + [vp] * 9
     lib.rb_launch_count.restype = ctypes.c_longlong
+    lib.rb_profile_enable.argtypes = [ctypes.c_int]
+    lib.rb_profile_cell_ms.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)]
+    lib.rb_fp64_peak.argtypes = [ctypes.POINTER(ctypes.c_double)]
     _LIB = lib
     return lib
 

@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+'''
+bench.py -- jac_g + hess_lag evaluations per second on the BASELINE.json workload.
+
+Workload (configs[1] / C2 / C5 of SURVEY.md s8d): scripts/race.py's racetrack, parametric
+(non-Euclidean) pose, quaternion drone, RK4 shooting with N = 70*7 = 490 intervals
+(nw = 10780).  One *step* evaluates a batch of independent problem instances -- seeded eval points
+x = clip(w0 + 1e-2*N(0,1)), lam_g ~ N(0,1), vehicle parameters x U[0.9, 1.1] -- and produces
+f, grad_f, g, jac_g values and hess_l values for every instance (one *eval* each).
+
+  value   evals/s with inputs and outputs resident in HBM (CUDA events, max over ranks)
+  e2e     evals/s through the C-ABI host entry point rb_nlp_eval_all with pinned HOST buffers,
+          host->device and device->host copies inside the timed region
+  --impl reference   the CPU path: the oracle's flat-tape interpreter (the execution model of
+          CasADi's SX virtual machine) on all host cores, one instance per thread
+
+Launch: python bench.py --gpus N --steps K --warmup W   (N > 1 under torch.distributed.run)
+'''
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+METRIC = 'jac_g+hess_lag evals/sec'
+UNIT = 'evals/s'
+CASE = 'race_param_rk4_drone'
+WORKLOAD = ('scripts/race.py racetrack, parametric (non-Euclidean) pose, quaternion drone, RK4 shooting '
+            'N=490 (C2), batch of seeded eval points x vehicle-parameter variants (C5 shape)')
+
+
+def _peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+class ClockSampler:
+    ''' nvidia-smi clocks / throttle reasons sampled while the timed region runs '''
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.gpu_index}', f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            p = [q.strip() for q in ln.split(',')]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                smax.append(float(p[2]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, p[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(nme)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None,
+                    sm_max_mhz=float(np.max(smax)) if smax else None,
+                    samples=len(sm), reasons=sorted(reasons))
+
+
+def make_inputs(st, vp0, B, seed0):
+    ''' eval points and vehicle variants, seeded per instance '''
+    X = np.empty((B, st.nw))
+    L = np.empty((B, st.ng))
+    VP = np.empty((B, len(vp0)))
+    for b in range(B):
+        rng = np.random.default_rng(seed0 + b)
+        X[b] = np.clip(st.w0 + 1e-2 * rng.standard_normal(st.nw), st.lbw, st.ubw)
+        L[b] = rng.standard_normal(st.ng)
+        scale = np.ones(len(vp0))
+        scale[[0, 2, 3, 4, 5, 6]] = np.random.default_rng(10_000 + seed0 + b).uniform(0.9, 1.1, 6)  # m, I1..3, l, k
+        VP[b] = vp0 * scale
+    return X, L, VP
+
+
+def algorithmic_bytes(st, n_consts=13):
+    ''' bytes one eval must move '''
+    n_pts = st.N * (st.K + 1)
+    return 8 * (st.nw + st.ng + n_pts * n_consts + st.ng + st.nw + st.nnz_jac + st.nnz_hess) + 8
+
+
+def cpu_port_rate(seconds_budget=12.0, nthreads=0, sample_intervals=49):
+    '''
+    the CPU path on a bounded sample: the oracle's interpreter on the first `sample_intervals`
+    of the 490 intervals (same track, same model; cost is linear in the interval count), rate
+    scaled by sample_intervals / 490.  Returns (evals/s for the full workload, cores, sample text).
+    '''
+    from cases import build_oracle
+    from oracle.nlp_functions import OracleNLP, max_threads
+    ref = build_oracle(CASE, N=sample_intervals // 7)
+    nlp = OracleNLP(ref)
+    cores = nthreads or len(os.sched_getaffinity(0))
+    cores = min(cores, max_threads())
+    rng = np.random.default_rng(0)
+    B = max(cores * 2, 8)
+    IN = np.zeros((B, nlp.n_in))
+    for b in range(B):
+        IN[b, :nlp.nw] = np.clip(ref.w0 + 1e-2 * rng.standard_normal(nlp.nw), ref.lbw, ref.ubw)
+        IN[b, nlp.nw:nlp.nw + nlp.ng] = rng.standard_normal(nlp.ng)
+        IN[b, -1] = 1.0
+    nlp.t_jac_g.batch(IN[:cores], cores)
+    t0 = time.time()
+    done = 0
+    while time.time() - t0 < seconds_budget:
+        nlp.t_grad_f.batch(IN, cores)
+        nlp.t_jac_g.batch(IN, cores)
+        nlp.t_hess_l.batch(IN, cores)
+        done += B
+    dt = time.time() - t0
+    full_N = 490
+    rate = done / dt * (ref.config.N / full_N)
+    sample = (f'oracle flat-tape interpreter (CasADi SX-VM execution model), {cores} threads, one instance '
+              f'per thread; {done} evals of the first {ref.config.N} of {full_N} intervals in {dt:.1f} s '
+              f'(tapes: jac {nlp.t_jac_g.n}, hess {nlp.t_hess_l.n} instructions), rate scaled by '
+              f'{ref.config.N}/{full_N}')
+    return rate, cores, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    rates = []
+    t0 = time.time()
+    sample = ''
+    cores = 1
+    for i in range(args.warmup + args.steps):
+        r, cores, sample = cpu_port_rate(seconds_budget=max(2.0, min(10.0, 60.0 / max(1, args.steps + args.warmup))))
+        if i >= args.warmup:
+            rates.append(r)
+    v = float(np.mean(rates))
+    line = dict(impl='reference', metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1e3 * (time.time() - t0) / max(1, args.steps + args.warmup),
+                higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64', data='synthetic',
+                config=dict(workload=WORKLOAD),
+                cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind='port', sample=sample),
+                e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=2048, help='problem instances per GPU per step')
+    ap.add_argument('--e2e-batch', type=int, default=256)
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+
+    if args.impl == 'reference':
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device (no CPU fallback)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    from cases import build_product
+    from aircraft_trajectory_optimization_b200.functions import NlpFunctions, load_library
+    from aircraft_trajectory_optimization_b200.models import vehicle_params
+    prod = build_product(CASE)
+    st = prod.structure
+    F = NlpFunctions(st, prod.vehicle_config, device=local_rank)
+    lib = load_library()
+    vp0 = vehicle_params(prod.vehicle_config)
+    B = args.batch
+    X, L, VP = make_inputs(st, vp0, B, seed0=rank * B)
+
+    f64 = dict(dtype=torch.float64, device=dev)
+    x_d = torch.from_numpy(X).to(dev)
+    l_d = torch.from_numpy(L).to(dev)
+    vp_d = torch.from_numpy(VP).to(dev)
+    sig_d = torch.ones(B, **f64)
+    f_d = torch.empty(B, **f64)
+    gf_d = torch.empty(B, st.nw, **f64)
+    g_d = torch.empty(B, st.ng, **f64)
+    j_d = torch.empty(B, st.nnz_jac, **f64)
+    h_d = torch.empty(B, st.nnz_hess, **f64)
+    scratch = torch.empty(lib.rb_eval_scratch_bytes(F.handle, B), dtype=torch.uint8, device=dev)
+
+    def step():
+        F.eval_device(x_d, l_d, sig_d, vp_d, None, f_d, gf_d, g_d, j_d, h_d, scratch)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    lib.rb_profile_enable(1)
+    l0 = lib.rb_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    launches = int(lib.rb_launch_count() - l0)
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    cell_ms, cell_n = ctypes.c_double(0), ctypes.c_int(0)
+    lib.rb_profile_cell_ms(ctypes.byref(cell_ms), ctypes.byref(cell_n))
+    lib.rb_profile_enable(0)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    value = world * B * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the host entry point (pinned host buffers) ----------------------------
+    Be = min(args.e2e_batch, B)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    hx, hl, hvp = pin(X[:Be]), pin(L[:Be]), pin(VP[:Be])
+    hsig = torch.ones(Be, dtype=torch.float64).pin_memory()
+    hf = torch.empty(Be, dtype=torch.float64).pin_memory()
+    hgf = torch.empty(Be, st.nw, dtype=torch.float64).pin_memory()
+    hg = torch.empty(Be, st.ng, dtype=torch.float64).pin_memory()
+    hj = torch.empty(Be, st.nnz_jac, dtype=torch.float64).pin_memory()
+    hh = torch.empty(Be, st.nnz_hess, dtype=torch.float64).pin_memory()
+    vptr = lambda t: ctypes.c_void_p(t.data_ptr())
+
+    def e2e_step():
+        rc = lib.rb_nlp_eval_all(F.handle, Be, vptr(hx), vptr(hvp), vptr(hsig), vptr(hl), vptr(hf), vptr(hgf),
+                                 vptr(hg), vptr(hj), vptr(hh))
+        if rc:
+            raise RuntimeError(lib.rb_last_error().decode())
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e2e_steps = max(3, args.steps // 2)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize(dev)
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_value = world * Be * e2e_steps / float(dt.item())
+    h2d = 8 * Be * (st.nw + st.ng + F.nvp + 1)
+    d2h = 8 * Be * (1 + st.nw + st.ng + st.nnz_jac + st.nnz_hess)
+    # spot check: the host path and the device path agree bit for bit on instance 0
+    assert np.array_equal(hh[0].numpy(), h_d[0].cpu().numpy()) and np.array_equal(hj[0].numpy(), j_d[0].cpu().numpy())
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        ab = algorithmic_bytes(st)
+        cell_avg_ms = cell_ms.value / max(1, cell_n.value)
+        achieved = ab * B / (cell_avg_ms * 1e-3) / 1e9
+        fp = ctypes.c_double(0)
+        lib.rb_fp64_peak(ctypes.byref(fp))
+        # straight-line fp64 instructions per eval: 4 jvp + 4 hvp per (interval, direction) thread
+        meta = __import__('aircraft_trajectory_optimization_b200.codegen', fromlist=['load_meta']).load_meta(prod.model.variant)
+        nv = st.nz + st.nu + 1
+        flop_eval = st.N * nv * 4 * (meta['ops']['jvp'] + meta['ops']['hvp'])
+        roofline = dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
+                        traffic=None, peak_source=peak_src, kernel='rk4_cells_kernel<PF_drone_quat_param_gr>',
+                        algorithmic_bytes_per_eval=ab, evals_per_launch=B, kernel_ms=cell_avg_ms,
+                        kernel_share_of_step=cell_ms.value / total_ms,
+                        fp64=dict(note='the shooting kernel is FP64-issue bound, not HBM bound: generated arithmetic '
+                                       'instructions per eval x evals / kernel time vs a measured FMA-rate peak',
+                                  arith_instr_per_eval=flop_eval, achieved_ginstr_s=flop_eval * B / (cell_avg_ms * 1e-3) / 1e9,
+                                  peak_gfma_s=fp.value * 1e3 / 2, frac=flop_eval * B / (cell_avg_ms * 1e-3) / (fp.value * 1e12 / 2)))
+        cpu = None
+        if not args.no_cpu:
+            r, cores, sample = cpu_port_rate()
+            cpu = dict(value=r, unit=UNIT, cores=cores, kind='port', sample=sample)
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=total_ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+                    dtype='f64', data='synthetic',
+                    config=dict(workload=WORKLOAD, instances_per_gpu_per_step=B, nw=st.nw, ng=st.ng,
+                                nnz_jac=st.nnz_jac, nnz_hess=st.nnz_hess,
+                                l2_policy=f'inputs+outputs per step {ab * B / 1e9:.2f} GB per GPU, larger than the 126 MB L2',
+                                parallelism=f'{world} x independent instance shards, no collective on the data path'),
+                    e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                             instances_per_step=Be, api='rb_nlp_eval_all (host buffers, pinned)'),
+                    gpu_launches=launches, clocks=clocks, roofline=roofline, cpu_baseline=cpu)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -127,6 +127,14 @@ int rb_nlp_hess_l(const rb_problem* p, int B, const double* x, const double* vp,
 int rb_nlp_eval_all(const rb_problem* p, int B, const double* x, const double* vp, const double* lam_f,
                     const double* lam_g, double* f, double* grad_f, double* g, double* jac, double* hess);
 
+/* instrumentation: when enabled, every rb_eval_batch brackets the interval-cell kernel (the dominant
+ * kernel) with CUDA events on the launching stream; rb_profile_cell_ms waits for them, returns the
+ * summed duration and the number of bracketed launches, and resets the counters. */
+int rb_profile_enable(int on);
+int rb_profile_cell_ms(double* total_ms, int* launches);
+/* measured FP64 FMA throughput of the current device in TFLOP/s (fma = 2 flop) */
+int rb_fp64_peak(double* tflops);
+
 /* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
 long long rb_launch_count(void);
 
