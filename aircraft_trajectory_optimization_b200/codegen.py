@@ -196,6 +196,14 @@ def generate_variant(variant: Variant, out_dir=GEN_DIR):
                                 + [f'Jv[{i}]' for i in range(len(pf.J))]
                                 + [f'Wv[{i}]' for i in range(len(pf.W))])
     parts.append(code)
+    code, ops['fJW_scatter'] = _emit_fn(
+        pf, 'fJW_scatter', [cx, 'const double* __restrict__ kb', cfc, cvp, 'double* __restrict__ f',
+                            'double* Jst', 'const int* __restrict__ tj', 'double* Hst',
+                            'const int* __restrict__ th'],
+        pf.f + pf.J_nodes + pf.W_nodes,
+        [f'f[{i}]' for i in range(nz)] + [f'Jst[tj[{i}]]' for i in range(len(pf.J))]
+        + [f'Hst[th[{i}]]' for i in range(len(pf.W))])
+    parts.append(code)
 
     def table(tname, vals):
         return f'  static constexpr signed char {tname}[{max(len(vals), 1)}] = {{' \

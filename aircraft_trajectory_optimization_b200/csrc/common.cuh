@@ -20,6 +20,12 @@ struct RbDev {
   const int32_t* cell_jslot;
   const int32_t* cell_hslot;
   int cell_nj, cell_nh, cell_ncp;
+  // collocation only: slot -> unique-entry template and the Legendre coefficient tables
+  const int32_t* tmpl_j;
+  const int32_t* tmpl_h;
+  const double* colloc_C;  // [8][8]  C[j][k] = l_j'(tau_k)
+  const double* colloc_D;  // [8]
+  const double* colloc_B;  // [8]
   int n_srow;
   const int32_t* srow_row;
   const int32_t* srow_kind;

@@ -73,8 +73,15 @@ cudaError_t launch_cells_t(const RbDev& d, const RbBatch& b, cudaStream_t st) {
     const long long blocks = (cells + CPB - 1) / CPB;
     rk4_cells_kernel<PF><<<(unsigned)blocks, RB_CELL_THREADS, 0, st>>>(d, b);
   } else {
-    const long long blocks = (cells + RB_COLLOC_CPB - 1) / RB_COLLOC_CPB;
-    colloc_cells_kernel<PF><<<(unsigned)blocks, RB_COLLOC_CPB * 8, 0, st>>>(d, b);
+    const long long blocks = (cells + RB_COLLOC_WPB - 1) / RB_COLLOC_WPB;
+    const size_t smem = sizeof(double) * RB_COLLOC_WPB * (size_t)colloc_cell_doubles<PF>(d.cell_nj, d.cell_nh);
+    static size_t configured = 0;
+    if (smem > configured) {
+      cudaError_t e = cudaFuncSetAttribute(colloc_cells_kernel<PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      configured = smem;
+    }
+    colloc_cells_kernel<PF><<<(unsigned)blocks, RB_COLLOC_WPB * 32, smem, st>>>(d, b);
   }
   g_launches++;
   return cudaGetLastError();
@@ -207,13 +214,11 @@ int rb_problem_create(const rb_problem_desc* s, rb_problem** out) {
     delete p;
     return fail("nw does not match N + N*(K+1)*(nz+2nu)");
   }
-  const size_t ncr = s->transcription == RB_RK4 ? (size_t)(p->nz + p->nu) : (size_t)s->cell_nj;  // colloc: see structure.py
   int rc = 0;
   rc |= upload(p, s->R, (size_t)p->nu, &d.R);
   rc |= upload(p, s->dR, (size_t)p->nu, &d.dR);
   rc |= upload(p, s->fc, (size_t)s->N * P * 13, &d.fc);
   const size_t nrow_tab = s->transcription == RB_RK4 ? (size_t)s->N * (p->nz + p->nu) : (size_t)s->N * RB_COLLOC_NCR(p->nz, p->nu);
-  (void)ncr;
   rc |= upload(p, s->cell_row, nrow_tab, &d.cell_row);
   rc |= upload(p, s->cell_coef, nrow_tab, &d.cell_coef);
   rc |= upload(p, s->cell_partner, nrow_tab, &d.cell_partner);
@@ -222,6 +227,17 @@ int rb_problem_create(const rb_problem_desc* s, rb_problem** out) {
   rc |= upload(p, s->cell_par, (size_t)s->N * s->cell_ncp, &d.cell_par);
   rc |= upload(p, s->cell_jslot, (size_t)s->N * s->cell_nj, &d.cell_jslot);
   rc |= upload(p, s->cell_hslot, (size_t)s->N * s->cell_nh, &d.cell_hslot);
+  if (s->transcription == RB_COLLOC) {
+    if (!s->tmpl_j || !s->tmpl_h || !s->colloc_C || !s->colloc_D || !s->colloc_B) {
+      rb_problem_destroy(p);
+      return fail("collocation problem without template / coefficient tables");
+    }
+    rc |= upload(p, s->tmpl_j, (size_t)s->n_tmpl_j, &d.tmpl_j);
+    rc |= upload(p, s->tmpl_h, (size_t)s->n_tmpl_h, &d.tmpl_h);
+    rc |= upload(p, s->colloc_C, (size_t)P * P, &d.colloc_C);
+    rc |= upload(p, s->colloc_D, (size_t)P, &d.colloc_D);
+    rc |= upload(p, s->colloc_B, (size_t)P, &d.colloc_B);
+  }
   if (s->n_srow > 0) {
     rc |= upload(p, s->srow_row, (size_t)s->n_srow, &d.srow_row);
     rc |= upload(p, s->srow_kind, (size_t)s->n_srow, &d.srow_kind);

@@ -34,6 +34,8 @@ class _Desc(ctypes.Structure):
         ('cell_row', _c_int_p), ('cell_coef', _c_dbl_p), ('cell_partner', _c_int_p), ('cell_pcoef', _c_dbl_p),
         ('cell_off', _c_dbl_p), ('cell_par', _c_dbl_p), ('cell_jslot', _c_int_p), ('cell_hslot', _c_int_p),
         ('cell_nj', ctypes.c_int), ('cell_nh', ctypes.c_int), ('cell_ncp', ctypes.c_int),
+        ('tmpl_j', _c_int_p), ('tmpl_h', _c_int_p), ('n_tmpl_j', ctypes.c_int), ('n_tmpl_h', ctypes.c_int),
+        ('colloc_C', _c_dbl_p), ('colloc_D', _c_dbl_p), ('colloc_B', _c_dbl_p),
         ('n_srow', ctypes.c_int), ('srow_row', _c_int_p), ('srow_kind', _c_int_p), ('srow_scale', _c_int_p),
         ('srow_var_ptr', _c_int_p), ('srow_var', _c_int_p), ('srow_jslot', _c_int_p),
         ('srow_form_ptr', _c_int_p), ('srow_coef_ptr', _c_int_p), ('srow_A', _c_dbl_p), ('srow_c', _c_dbl_p),
@@ -236,6 +238,10 @@ class NlpFunctions:
         d.cell_pcoef, d.cell_off, d.cell_par = f64(c['pcoef']), f64(c['off']), f64(c['par'])
         d.cell_jslot, d.cell_hslot = i32(c['jslot']), i32(c['hslot'])
         d.cell_nj, d.cell_nh, d.cell_ncp = c['nj'], c['nh'], c['ncp']
+        if c.get('tmpl_j') is not None:
+            d.tmpl_j, d.tmpl_h = i32(c['tmpl_j']), i32(c['tmpl_h'])
+            d.n_tmpl_j, d.n_tmpl_h = len(c['tmpl_j']), len(c['tmpl_h'])
+            d.colloc_C, d.colloc_D, d.colloc_B = f64(c['C']), f64(c['D']), f64(c['B'])
         d.n_srow = s['n']
         d.srow_row, d.srow_kind, d.srow_scale = i32(s['row']), i32(s['kind']), i32(s['scale'])
         d.srow_var_ptr, d.srow_var, d.srow_jslot = i32(s['var_ptr']), i32(s['var']), i32(s['jslot'])

@@ -16,7 +16,7 @@ class PythonMsg:
     ''' dataclass base that refuses to grow new attributes after construction '''
 
     def __setattr__(self, key, value):
-        if not hasattr(self, key):
+        if not hasattr(self, key) and key not in getattr(self, '__dataclass_fields__', {}):
             raise TypeError(f'Not allowed to add new field "{key}" to class {self}')
         object.__setattr__(self, key, value)
 

@@ -300,6 +300,8 @@ def _assemble(sb: StructureBuilder, jent, hent) -> NLPStructure:
                 pcoef=f64(sb.cell_pcoef), off=f64(sb.cell_off), par=f64(sb.cell_par),
                 jslot=i32(cell_jslot), hslot=i32(cell_hslot), nj=sb.cell_nj, nh=sb.cell_nh,
                 ncp=sb.cell_par.shape[1])
+    if sb.transcription == COLLOC:
+        cell.update(tmpl_j=i32(sb.tmpl_j), tmpl_h=i32(sb.tmpl_h), C=f64(sb.C), D=f64(sb.D), B=f64(sb.B))
     return NLPStructure(
         transcription=sb.transcription, variant=sb.variant, N=sb.N, K=sb.K, nz=sb.nz, nu=sb.nu,
         nw=nw, ng=ng, R=f64(sb.R), dR=f64(sb.dR), fc=None if sb.fc is None else f64(sb.fc),

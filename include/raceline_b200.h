@@ -56,6 +56,14 @@ typedef struct rb_problem_desc {
   const int32_t* cell_hslot;     /* flattened local-Hessian-slot  -> CCS position (-1: not stored) */
   int cell_nj, cell_nh;          /* local slots per cell in the two tables */
   int cell_ncp;
+  /* collocation only (NULL / 0 for RK4): local contribution slot -> unique local entry id, and the
+   * Legendre coefficient tables of drone3d/utils/discretization_utils.py:6-34 */
+  const int32_t* tmpl_j;         /* [n_tmpl_j] */
+  const int32_t* tmpl_h;         /* [n_tmpl_h] */
+  int n_tmpl_j, n_tmpl_h;
+  const double* colloc_C;        /* [(K+1)*(K+1)] C[j][k] = l_j'(tau_k), row-major */
+  const double* colloc_D;        /* [K+1] */
+  const double* colloc_B;        /* [K+1] */
 
   /* ---- simple rows: g = scale * sum_m (sum_i A[m][i] w[idx_i] + c[m])^(1 or 2) ------------- */
   int n_srow;
