@@ -1,0 +1,592 @@
+// Batched block-tridiagonal + border factor/solve of the interior-point KKT system.
+//
+// What it replaces: the sparse symmetric-indefinite solve IPOPT performs on every iteration inside
+// `self.solver(x0=..., ...)` (drone3d/raceline/base_raceline.py:160-165; linear solver chosen at
+// :765-787).  The matrix is
+//        [ W + diag(dx_diag)     J'        ]
+//        [ J                     diag(neg_d) ]
+// given by the CCS values of hess_l / jac_g and two diagonals; the grouping of unknowns into interval
+// blocks + border is computed on the host (aircraft_trajectory_optimization_b200/kkt.py, which also
+// documents the tables).
+//
+// One CTA per problem instance.  Forward sweep over the N interval blocks: assemble the diagonal block
+// in shared memory, subtract the Schur carry of the previous block, invert it in place (Gauss-Jordan,
+// partial pivoting, one pivot column per step), apply the inverse to the 1 + nb right-hand sides and to
+// the coupling block, form the carry for the next block.  Backward sweep: x_n = z_n - YL_n x_{n+1}.
+// Border: dense nb x nb Schur complement, inverted the same way.  Factors (block inverses, YL, border
+// columns, border inverse) stay in HBM so that further right-hand sides (iterative refinement) cost a
+// solve, not a factorisation.
+#pragma once
+#include "common.cuh"
+
+#define RB_KKT_THREADS 256
+
+struct RbKktDev {
+  int nw, ng, N, nb, bmax, mmax, qmax, n_bG;
+  const int32_t *blk_ptr, *unk;
+  const int32_t *dA_ptr, *dA_src, *dA_pos;
+  const int32_t *cr_ptr, *cr, *cc_ptr, *cc, *cL_ptr, *cL_src, *cL_pos;
+  const int32_t *bE_ptr, *bE_src, *bE_row, *bE_col;      // grouped by block
+  const int32_t *bEc_ptr, *bEc_idx, *bE_blk;             // the same entries grouped by border column
+  const int32_t *bG_src, *bG_pos;
+  // K v products: CCS (column-wise) and CSR-ordered views of jac_g and of the upper triangle of hess_l
+  const int32_t *j_colptr, *j_row, *j_rowptr, *j_col, *j_perm;
+  const int32_t *h_colptr, *h_row, *h_rowptr, *h_col, *h_perm;
+};
+
+struct RbKktBatch {
+  int B;
+  int nnzh, nnzj;
+  const double *hess, *jac, *dx_diag, *neg_d;   // [B][nnzh], [B][nnzj], [B][nw], [B][ng]
+  const double* rhs;                            // [B][nw+ng]
+  double* sol;                                  // [B][nw+ng]
+  double* Sinv;                                 // [B][N][bmax*bmax]
+  double* YL;                                   // [B][N][bmax*mmax]
+  double* X;                                    // [B][N][bmax*(1+nb)]  z, then x; columns 1.. = T^-1 E
+  double* Xr;                                   // [B][N][bmax]         single column for re-solves
+  double* SB;                                   // [B][nb*nb] inverse of the border Schur complement
+  int* status;                                  // [B][2] vanishing pivots met, negative eigenvalues
+};
+
+struct KktVals {
+  const double *hess, *jac, *dx, *nd;
+};
+
+__device__ __forceinline__ double kkt_val(const KktVals& v, int32_t src) {
+  const int kind = (src >> 28) & 3;
+  const int idx = src & 0x0fffffff;
+  const double* base = kind == 0 ? v.hess : (kind == 1 ? v.jac : (kind == 2 ? v.dx : v.nd));
+  return base[idx];
+}
+
+__device__ __forceinline__ double kkt_diag(const KktVals& v, int u, int nw) {
+  return u < nw ? v.dx[u] : v.nd[u - nw];
+}
+
+// In-place inverse of the SYMMETRIC b x b matrix M (row-major, leading dimension LD, shared memory) by
+// Gauss-Jordan sweeps with Bunch-Parlett pivoting: at every step the largest remaining diagonal entry
+// is compared with the largest remaining off-diagonal entry; a 1x1 pivot is taken when
+// |diag| >= alpha |offdiag| (alpha = (1 + sqrt 17) / 8), otherwise the 2x2 pivot spanned by the largest
+// off-diagonal entry.  Pivots are taken in place (symmetric pivoting only chooses the order), so no
+// permutation has to be undone.  The pivot signs give the inertia: *neg accumulates the number of
+// negative eigenvalues (a 2x2 pivot chosen this way has exactly one); the return value counts
+// vanishing pivots.  The search for the next pivot is fused into the update pass.
+struct KktPivot {
+  double vd, vo;   // largest |diagonal|, largest |off-diagonal| among the unswept part
+  int kd, io, jo;
+};
+
+__device__ __forceinline__ void kkt_pivot_merge(KktPivot& a, double vd, int kd, double vo, int io, int jo) {
+  if (vd > a.vd || (vd == a.vd && kd < a.kd)) {
+    a.vd = vd;
+    a.kd = kd;
+  }
+  if (vo > a.vo || (vo == a.vo && (io < a.io || (io == a.io && jo < a.jo)))) {
+    a.vo = vo;
+    a.io = io;
+    a.jo = jo;
+  }
+}
+
+// block-wide reduction of the per-thread candidates; the result lands in *out (shared memory)
+__device__ void kkt_pivot_reduce(KktPivot mine, KktPivot* warp_slots, KktPivot* out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double vd = __shfl_xor_sync(0xffffffffu, mine.vd, o);
+    const int kd = __shfl_xor_sync(0xffffffffu, mine.kd, o);
+    const double vo = __shfl_xor_sync(0xffffffffu, mine.vo, o);
+    const int io = __shfl_xor_sync(0xffffffffu, mine.io, o);
+    const int jo = __shfl_xor_sync(0xffffffffu, mine.jo, o);
+    kkt_pivot_merge(mine, vd, kd, vo, io, jo);
+  }
+  if (lane == 0) warp_slots[warp] = mine;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    KktPivot r = warp_slots[0];
+    for (int w = 1; w < nwarps; ++w) kkt_pivot_merge(r, warp_slots[w].vd, warp_slots[w].kd, warp_slots[w].vo, warp_slots[w].io, warp_slots[w].jo);
+    *out = r;
+  }
+  __syncthreads();
+}
+
+__device__ int kkt_sym_invert(double* M, int LD, int b, double* colp, double* rowp, double* colq, double* rowq,
+                              int* swept, KktPivot* slots, int* neg) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  KktPivot* cur = slots + nwarps;
+  const double alpha = 0.6403882032022076;
+  int bad = 0, nneg = 0;
+  for (int i = tid; i < b; i += blockDim.x) swept[i] = 0;
+  // initial search
+  KktPivot mine{-1.0, -1.0, 0x7fffffff, 0x7fffffff, 0x7fffffff};
+  for (int i = warp; i < b; i += nwarps)
+    for (int j = lane; j < b; j += 32) {
+      if (j < i) continue;
+      const double a = fabs(M[i * LD + j]);
+      if (i == j) kkt_pivot_merge(mine, a, i, -1.0, 0x7fffffff, 0x7fffffff);
+      else kkt_pivot_merge(mine, -1.0, 0x7fffffff, a, i, j);
+    }
+  __syncthreads();
+  kkt_pivot_reduce(mine, slots, cur);
+  int remaining = b;
+  while (remaining > 0) {
+    const KktPivot pv = *cur;
+    const bool two = remaining > 1 && !(pv.vd >= alpha * pv.vo);
+    mine = KktPivot{-1.0, -1.0, 0x7fffffff, 0x7fffffff, 0x7fffffff};
+    if (!two) {
+      const int k = pv.kd;
+      double d = M[k * LD + k];
+      if (!(fabs(d) > 1e-250)) {
+        d = 1e-250;
+        bad++;
+      }
+      if (d < 0) nneg++;
+      const double di = 1.0 / d;
+      for (int j = tid; j < b; j += blockDim.x) {
+        colp[j] = M[j * LD + k];
+        rowp[j] = M[k * LD + j] * di;
+      }
+      if (tid == 0) swept[k] = 1;
+      __syncthreads();
+      for (int i = warp; i < b; i += nwarps) {
+        const double ci = colp[i];
+        const bool ui = !swept[i];
+        for (int j = lane; j < b; j += 32) {
+          double v;
+          if (i == k) v = (j == k) ? di : rowp[j];
+          else if (j == k) v = -ci * di;
+          else v = M[i * LD + j] - ci * rowp[j];
+          M[i * LD + j] = v;
+          if (ui && j >= i && !swept[j]) {
+            const double a = fabs(v);
+            if (i == j) kkt_pivot_merge(mine, a, i, -1.0, 0x7fffffff, 0x7fffffff);
+            else kkt_pivot_merge(mine, -1.0, 0x7fffffff, a, i, j);
+          }
+        }
+      }
+      remaining -= 1;
+    } else {
+      const int p = pv.io, q = pv.jo;
+      const double epp = M[p * LD + p], epq = M[p * LD + q], eqq = M[q * LD + q];
+      double det = epp * eqq - epq * epq;
+      if (!(fabs(det) > 1e-250)) {
+        det = -1e-250;
+        bad++;
+      }
+      nneg++;   // |epq| dominates the diagonal: det < 0, one eigenvalue of each sign
+      if (det > 0 && epp + eqq < 0) nneg++;   // (cannot happen with the pivot rule; kept for safety)
+      else if (det > 0) nneg--;
+      const double i00 = eqq / det, i01 = -epq / det, i11 = epp / det;
+      for (int j = tid; j < b; j += blockDim.x) {
+        const double ap = M[p * LD + j], aq = M[q * LD + j];
+        colp[j] = M[j * LD + p];
+        colq[j] = M[j * LD + q];
+        rowp[j] = i00 * ap + i01 * aq;
+        rowq[j] = i01 * ap + i11 * aq;
+      }
+      if (tid == 0) {
+        swept[p] = 1;
+        swept[q] = 1;
+      }
+      __syncthreads();
+      for (int i = warp; i < b; i += nwarps) {
+        const double cp = colp[i], cq = colq[i];
+        const bool ui = !swept[i];
+        for (int j = lane; j < b; j += 32) {
+          double v;
+          if (i == p) v = (j == p) ? i00 : ((j == q) ? i01 : rowp[j]);
+          else if (i == q) v = (j == p) ? i01 : ((j == q) ? i11 : rowq[j]);
+          else if (j == p) v = -(cp * i00 + cq * i01);
+          else if (j == q) v = -(cp * i01 + cq * i11);
+          else v = M[i * LD + j] - cp * rowp[j] - cq * rowq[j];
+          M[i * LD + j] = v;
+          if (ui && j >= i && !swept[j]) {
+            const double a = fabs(v);
+            if (i == j) kkt_pivot_merge(mine, a, i, -1.0, 0x7fffffff, 0x7fffffff);
+            else kkt_pivot_merge(mine, -1.0, 0x7fffffff, a, i, j);
+          }
+        }
+      }
+      remaining -= 2;
+    }
+    __syncthreads();
+    if (remaining > 0) kkt_pivot_reduce(mine, slots, cur);
+  }
+  *neg += nneg;
+  return bad;
+}
+
+struct KktSmem {
+  double *M, *Yr, *Zs, *Lc, *YLs, *carry, *rcarry, *colp, *rowp, *colq, *rowq;
+  KktPivot* slots;
+  int* swept;
+};
+
+__host__ __device__ inline size_t kkt_smem_doubles(int bmax, int nb, int mmax, int qmax) {
+  const int LD = bmax | 1, nrhs = 1 + nb, nbb = nb > bmax ? nb : bmax;
+  const int LDm = nbb | 1;
+  size_t n = (size_t)nbb * LDm;               // M (also hosts the border matrix)
+  n += 2 * (size_t)nbb * nrhs;                // Yr, Zs
+  n += (size_t)mmax * qmax;                   // Lc
+  n += (size_t)bmax * mmax;                   // YLs
+  n += (size_t)mmax * mmax;                   // carry
+  n += (size_t)mmax * nrhs;                   // rcarry
+  n += 4 * (size_t)nbb;                       // colp, rowp, colq, rowq
+  (void)LD;
+  return n;
+}
+
+__host__ __device__ inline size_t kkt_smem_bytes(int bmax, int nb, int mmax, int qmax) {
+  const int nbb = nb > bmax ? nb : bmax;
+  return kkt_smem_doubles(bmax, nb, mmax, qmax) * sizeof(double) + (RB_KKT_THREADS / 32 + 1) * sizeof(KktPivot) +
+         ((size_t)nbb + 4) * sizeof(int);
+}
+
+__device__ inline KktSmem kkt_carve(double* s, int bmax, int nb, int mmax, int qmax) {
+  const int nrhs = 1 + nb, nbb = nb > bmax ? nb : bmax, LDm = nbb | 1;
+  KktSmem k;
+  k.M = s; s += (size_t)nbb * LDm;
+  k.Yr = s; s += (size_t)nbb * nrhs;
+  k.Zs = s; s += (size_t)nbb * nrhs;
+  k.Lc = s; s += (size_t)mmax * qmax;
+  k.YLs = s; s += (size_t)bmax * mmax;
+  k.carry = s; s += (size_t)mmax * mmax;
+  k.rcarry = s; s += (size_t)mmax * nrhs;
+  k.colp = s; s += nbb;
+  k.rowp = s; s += nbb;
+  k.colq = s; s += nbb;
+  k.rowq = s; s += nbb;
+  k.slots = reinterpret_cast<KktPivot*>(s);
+  k.swept = reinterpret_cast<int*>(k.slots + RB_KKT_THREADS / 32 + 1);
+  return k;
+}
+
+__global__ void __launch_bounds__(RB_KKT_THREADS)
+kkt_factor_solve_kernel(const RbKktDev d, const RbKktBatch bt) {
+  extern __shared__ double kkt_smem[];
+  const int p = blockIdx.x;
+  if (p >= bt.B) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int nk = d.nw + d.ng, nrhs = 1 + d.nb, bmax = d.bmax, mmax = d.mmax, qmax = d.qmax, N = d.N;
+  const int nbb = d.nb > bmax ? d.nb : bmax;
+  const int LD = nbb | 1;
+  KktSmem s = kkt_carve(kkt_smem, bmax, d.nb, mmax, qmax);
+  KktVals v{bt.hess + (size_t)p * bt.nnzh, bt.jac + (size_t)p * bt.nnzj, bt.dx_diag + (size_t)p * d.nw,
+            bt.neg_d + (size_t)p * d.ng};
+  const double* __restrict__ rhs = bt.rhs + (size_t)p * nk;
+  double* __restrict__ sol = bt.sol + (size_t)p * nk;
+  double* __restrict__ Sinv_g = bt.Sinv + (size_t)p * N * bmax * bmax;
+  double* __restrict__ YL_g = bt.YL + (size_t)p * N * bmax * mmax;
+  double* __restrict__ X_g = bt.X + (size_t)p * N * bmax * nrhs;
+  int bad = 0, neg = 0;
+  int m_prev = 0;
+  const int32_t* cr_prev = nullptr;
+
+  // ------------------------------------------------------------------------------ forward sweep
+  for (int n = 0; n < N; ++n) {
+    const int u0 = d.blk_ptr[n], b = d.blk_ptr[n + 1] - u0;
+    const int32_t* __restrict__ unk = d.unk + u0;
+    for (int i = tid; i < b * LD; i += blockDim.x) s.M[i] = 0.0;
+    for (int i = tid; i < b * nrhs; i += blockDim.x) s.Yr[i] = 0.0;
+    __syncthreads();
+    for (int e = d.dA_ptr[n] + tid; e < d.dA_ptr[n + 1]; e += blockDim.x) {
+      const int pos = d.dA_pos[e];
+      const int r = pos / bmax, c = pos - r * bmax;
+      s.M[r * LD + c] = kkt_val(v, d.dA_src[e]);
+    }
+    for (int e = d.bE_ptr[n] + tid; e < d.bE_ptr[n + 1]; e += blockDim.x)
+      s.Yr[d.bE_row[e] * nrhs + 1 + d.bE_col[e]] = kkt_val(v, d.bE_src[e]);
+    __syncthreads();
+    for (int i = tid; i < b; i += blockDim.x) {
+      s.M[i * LD + i] += kkt_diag(v, unk[i], d.nw);
+      s.Yr[i * nrhs] = rhs[unk[i]];
+    }
+    __syncthreads();
+    if (n > 0) {
+      for (int i = tid; i < m_prev * m_prev; i += blockDim.x) {
+        const int a = i / m_prev, c = i - a * m_prev;
+        s.M[cr_prev[a] * LD + cr_prev[c]] -= s.carry[a * mmax + c];
+      }
+      for (int i = tid; i < m_prev * nrhs; i += blockDim.x) {
+        const int a = i / nrhs, r = i - a * nrhs;
+        s.Yr[cr_prev[a] * nrhs + r] -= s.rcarry[a * nrhs + r];
+      }
+      __syncthreads();
+    }
+    bad += kkt_sym_invert(s.M, LD, b, s.colp, s.rowp, s.colq, s.rowq, s.swept, s.slots, &neg);
+
+    // z = S^-1 y  (row i per warp, right-hand sides across lanes)
+    for (int i = warp; i < b; i += nwarps) {
+      for (int r = lane; r < nrhs; r += 32) {
+        double acc = 0.0;
+        for (int j = 0; j < b; ++j) acc += s.M[i * LD + j] * s.Yr[j * nrhs + r];
+        s.Zs[i * nrhs + r] = acc;
+        X_g[((size_t)n * bmax + i) * nrhs + r] = acc;
+      }
+    }
+    // keep the inverse
+    if (bt.Sinv) {
+      for (int i = warp; i < b; i += nwarps)
+        for (int j = lane; j < b; j += 32) Sinv_g[((size_t)n * bmax + i) * bmax + j] = s.M[i * LD + j];
+    }
+    if (n < N - 1) {
+      const int m = d.cr_ptr[n + 1] - d.cr_ptr[n], q = d.cc_ptr[n + 1] - d.cc_ptr[n];
+      const int32_t* __restrict__ cc = d.cc + d.cc_ptr[n];
+      for (int i = tid; i < m * qmax; i += blockDim.x) s.Lc[i] = 0.0;
+      __syncthreads();
+      for (int e = d.cL_ptr[n] + tid; e < d.cL_ptr[n + 1]; e += blockDim.x) s.Lc[d.cL_pos[e]] = kkt_val(v, d.cL_src[e]);
+      __syncthreads();
+      // YL = S^-1[:, cc] Lc'   (b x m): rows across lanes, coupling rows across warps
+      for (int a = warp; a < m; a += nwarps) {
+        for (int i = lane; i < b; i += 32) {
+          double acc = 0.0;
+          for (int t = 0; t < q; ++t) acc += s.M[i * LD + cc[t]] * s.Lc[a * qmax + t];
+          s.YLs[i * mmax + a] = acc;
+          YL_g[((size_t)n * bmax + i) * mmax + a] = acc;
+        }
+      }
+      __syncthreads();
+      // carry = Lc YL[cc, :]  (m x m),  rcarry = Lc z[cc, :]  (m x nrhs)
+      for (int i = tid; i < m * m; i += blockDim.x) {
+        const int a = i / m, c = i - a * m;
+        double acc = 0.0;
+        for (int t = 0; t < q; ++t) acc += s.Lc[a * qmax + t] * s.YLs[cc[t] * mmax + c];
+        s.carry[a * mmax + c] = acc;
+      }
+      for (int i = tid; i < m * nrhs; i += blockDim.x) {
+        const int a = i / nrhs, r = i - a * nrhs;
+        double acc = 0.0;
+        for (int t = 0; t < q; ++t) acc += s.Lc[a * qmax + t] * s.Zs[cc[t] * nrhs + r];
+        s.rcarry[a * nrhs + r] = acc;
+      }
+      m_prev = m;
+      cr_prev = d.cr + d.cr_ptr[n];
+    }
+    __syncthreads();
+  }
+
+  // ------------------------------------------------------------------------------ backward sweep
+  // Zs holds x_{N-1} (= z_{N-1}); walk down, keeping the current block's solution in Zs
+  for (int n = N - 2; n >= 0; --n) {
+    const int b = d.blk_ptr[n + 1] - d.blk_ptr[n];
+    const int m = d.cr_ptr[n + 1] - d.cr_ptr[n];
+    const int32_t* __restrict__ cr = d.cr + d.cr_ptr[n];
+    // gather the needed rows of x_{n+1}
+    for (int i = tid; i < m * nrhs; i += blockDim.x) {
+      const int a = i / nrhs, r = i - a * nrhs;
+      s.rcarry[a * nrhs + r] = s.Zs[cr[a] * nrhs + r];
+    }
+    __syncthreads();
+    for (int i = warp; i < b; i += nwarps) {
+      const double* __restrict__ yl = YL_g + ((size_t)n * bmax + i) * mmax;
+      for (int r = lane; r < nrhs; r += 32) {
+        double acc = X_g[((size_t)n * bmax + i) * nrhs + r];
+        for (int a = 0; a < m; ++a) acc -= yl[a] * s.rcarry[a * nrhs + r];
+        s.Zs[i * nrhs + r] = acc;
+        X_g[((size_t)n * bmax + i) * nrhs + r] = acc;
+      }
+    }
+    __syncthreads();
+  }
+
+  // ------------------------------------------------------------------------------ border
+  const int nb = d.nb;
+  double* xb = s.colp;   // reused after the inversion below
+  if (nb > 0) {
+    const int ub0 = d.blk_ptr[N];
+    const int32_t* __restrict__ unkb = d.unk + ub0;
+    for (int i = tid; i < nb * LD; i += blockDim.x) s.M[i] = 0.0;
+    __syncthreads();
+    for (int e = tid; e < d.n_bG; e += blockDim.x) {
+      const int pos = d.bG_pos[e];
+      const int r = pos / nb, c = pos - r * nb;
+      s.M[r * LD + c] = kkt_val(v, d.bG_src[e]);
+    }
+    __syncthreads();
+    for (int i = tid; i < nb; i += blockDim.x) {
+      s.M[i * LD + i] += kkt_diag(v, unkb[i], d.nw);
+      s.Yr[i] = rhs[unkb[i]];
+    }
+    __syncthreads();
+    // G -= E' X_E, rb -= E' x_T : one border column j per warp, lanes over the nrhs columns of X
+    for (int j = warp; j < nb; j += nwarps) {
+      for (int r = lane; r < nrhs; r += 32) {
+        double acc = 0.0;
+        for (int t = d.bEc_ptr[j]; t < d.bEc_ptr[j + 1]; ++t) {
+          const int e = d.bEc_idx[t];
+          acc += kkt_val(v, d.bE_src[e]) * X_g[((size_t)d.bE_blk[e] * bmax + d.bE_row[e]) * nrhs + r];
+        }
+        if (r == 0) s.Yr[j] -= acc;
+        else s.M[j * LD + (r - 1)] -= acc;
+      }
+    }
+    __syncthreads();
+    bad += kkt_sym_invert(s.M, LD, nb, s.colp, s.rowp, s.colq, s.rowq, s.swept, s.slots, &neg);
+    if (bt.SB)
+      for (int i = tid; i < nb * nb; i += blockDim.x) {
+        const int r = i / nb, c = i - r * nb;
+        bt.SB[(size_t)p * nb * nb + i] = s.M[r * LD + c];
+      }
+    __syncthreads();   // colp is free again
+    for (int i = tid; i < nb; i += blockDim.x) {
+      double acc = 0.0;
+      for (int j = 0; j < nb; ++j) acc += s.M[i * LD + j] * s.Yr[j];
+      xb[i] = acc;
+      sol[unkb[i]] = acc;
+    }
+    __syncthreads();
+  }
+  // x = x_T - X_E x_b, scattered back to the (w, g) order
+  const int nchain = d.blk_ptr[N];
+  for (int t = tid; t < nchain; t += blockDim.x) {
+    // block of unknown t: binary search over blk_ptr
+    int lo = 0, hi = N - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (d.blk_ptr[mid] <= t) lo = mid; else hi = mid - 1;
+    }
+    const int i = t - d.blk_ptr[lo];
+    const double* __restrict__ x = X_g + ((size_t)lo * bmax + i) * nrhs;
+    double acc = x[0];
+    for (int j = 0; j < nb; ++j) acc -= x[1 + j] * xb[j];
+    sol[d.unk[t]] = acc;
+  }
+  if (tid == 0 && bt.status) {
+    bt.status[2 * p] = bad;
+    bt.status[2 * p + 1] = neg;
+  }
+}
+
+// Another right-hand side with the stored factors (iterative refinement, corrections).
+// E values are re-gathered from hess / jac, which must be unchanged since the factorisation.
+__global__ void __launch_bounds__(RB_KKT_THREADS)
+kkt_resolve_kernel(const RbKktDev d, const RbKktBatch bt) {
+  extern __shared__ double kkt_smem[];
+  const int p = blockIdx.x;
+  if (p >= bt.B) return;
+  const int tid = threadIdx.x;
+  const int nk = d.nw + d.ng, nrhs = 1 + d.nb, bmax = d.bmax, mmax = d.mmax, N = d.N, nb = d.nb;
+  const int nbb = nb > bmax ? nb : bmax;
+  double* y = kkt_smem;             // [nbb] current block rhs / z
+  double* xn = y + nbb;             // [nbb] solution of the block above (backward)
+  double* rc = xn + nbb;            // [mmax] carry
+  double* xb = rc + mmax;           // [nb]
+  KktVals v{bt.hess + (size_t)p * bt.nnzh, bt.jac + (size_t)p * bt.nnzj, bt.dx_diag + (size_t)p * d.nw,
+            bt.neg_d + (size_t)p * d.ng};
+  const double* __restrict__ rhs = bt.rhs + (size_t)p * nk;
+  double* __restrict__ sol = bt.sol + (size_t)p * nk;
+  const double* __restrict__ Sinv_g = bt.Sinv + (size_t)p * N * bmax * bmax;
+  const double* __restrict__ YL_g = bt.YL + (size_t)p * N * bmax * mmax;
+  const double* __restrict__ X_g = bt.X + (size_t)p * N * bmax * nrhs;
+  double* __restrict__ Xr = bt.Xr + (size_t)p * N * bmax;
+  int m_prev = 0;
+  const int32_t* cr_prev = nullptr;
+  for (int n = 0; n < N; ++n) {
+    const int u0 = d.blk_ptr[n], b = d.blk_ptr[n + 1] - u0;
+    for (int i = tid; i < b; i += blockDim.x) y[i] = rhs[d.unk[u0 + i]];
+    __syncthreads();
+    if (n > 0) {
+      for (int a = tid; a < m_prev; a += blockDim.x) y[cr_prev[a]] -= rc[a];
+      __syncthreads();
+    }
+    for (int i = tid; i < b; i += blockDim.x) {
+      const double* __restrict__ si = Sinv_g + ((size_t)n * bmax + i) * bmax;
+      double acc = 0.0;
+      for (int j = 0; j < b; ++j) acc += si[j] * y[j];
+      Xr[(size_t)n * bmax + i] = acc;
+    }
+    if (n < N - 1) {
+      const int m = d.cr_ptr[n + 1] - d.cr_ptr[n];
+      // L_n S_n^-1 y_n = YL_n' y_n   (S_n is symmetric)
+      for (int a = tid; a < m; a += blockDim.x) {
+        double acc = 0.0;
+        for (int i = 0; i < b; ++i) acc += YL_g[((size_t)n * bmax + i) * mmax + a] * y[i];
+        rc[a] = acc;
+      }
+      m_prev = m;
+      cr_prev = d.cr + d.cr_ptr[n];
+    }
+    __syncthreads();
+  }
+  {
+    const int b = d.blk_ptr[N] - d.blk_ptr[N - 1];
+    for (int i = tid; i < b; i += blockDim.x) xn[i] = Xr[(size_t)(N - 1) * bmax + i];
+    __syncthreads();
+  }
+  for (int n = N - 2; n >= 0; --n) {
+    const int b = d.blk_ptr[n + 1] - d.blk_ptr[n];
+    const int m = d.cr_ptr[n + 1] - d.cr_ptr[n];
+    const int32_t* __restrict__ cr = d.cr + d.cr_ptr[n];
+    for (int a = tid; a < m; a += blockDim.x) rc[a] = xn[cr[a]];
+    __syncthreads();
+    for (int i = tid; i < b; i += blockDim.x) {
+      const double* __restrict__ yl = YL_g + ((size_t)n * bmax + i) * mmax;
+      double acc = Xr[(size_t)n * bmax + i];
+      for (int a = 0; a < m; ++a) acc -= yl[a] * rc[a];
+      xn[i] = acc;
+      Xr[(size_t)n * bmax + i] = acc;
+    }
+    __syncthreads();
+  }
+  if (nb > 0) {
+    const int32_t* __restrict__ unkb = d.unk + d.blk_ptr[N];
+    for (int j = tid; j < nb; j += blockDim.x) {
+      double acc = rhs[unkb[j]];
+      for (int t = d.bEc_ptr[j]; t < d.bEc_ptr[j + 1]; ++t) {
+        const int e = d.bEc_idx[t];
+        acc -= kkt_val(v, d.bE_src[e]) * Xr[(size_t)d.bE_blk[e] * bmax + d.bE_row[e]];
+      }
+      y[j] = acc;
+    }
+    __syncthreads();
+    for (int i = tid; i < nb; i += blockDim.x) {
+      double acc = 0.0;
+      for (int j = 0; j < nb; ++j) acc += bt.SB[(size_t)p * nb * nb + i * nb + j] * y[j];
+      xb[i] = acc;
+      sol[unkb[i]] = acc;
+    }
+    __syncthreads();
+  }
+  const int nchain = d.blk_ptr[N];
+  for (int t = tid; t < nchain; t += blockDim.x) {
+    int lo = 0, hi = N - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (d.blk_ptr[mid] <= t) lo = mid; else hi = mid - 1;
+    }
+    const int i = t - d.blk_ptr[lo];
+    const double* __restrict__ x = X_g + ((size_t)lo * bmax + i) * nrhs;
+    double acc = Xr[(size_t)lo * bmax + i];
+    for (int j = 0; j < nb; ++j) acc -= x[1 + j] * xb[j];
+    sol[d.unk[t]] = acc;
+  }
+}
+
+// out = K v  for the KKT matrix above (used for residuals in iterative refinement and for tests).
+// One thread per output entry; fixed summation order (deterministic).
+__global__ void kkt_matvec_kernel(const RbKktDev d, const RbKktBatch bt, const double* __restrict__ vec,
+                                  double* __restrict__ out) {
+  const int nk = d.nw + d.ng;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)bt.B * nk) return;
+  const int p = (int)(t / nk);
+  const int i = (int)(t - (long long)p * nk);
+  const double* __restrict__ hess = bt.hess + (size_t)p * bt.nnzh;
+  const double* __restrict__ jac = bt.jac + (size_t)p * bt.nnzj;
+  const double* __restrict__ x = vec + (size_t)p * nk;
+  double acc;
+  if (i < d.nw) {
+    acc = bt.dx_diag[(size_t)p * d.nw + i] * x[i];
+    for (int k = d.h_colptr[i]; k < d.h_colptr[i + 1]; ++k) acc += hess[k] * x[d.h_row[k]];          // rows <= i
+    for (int k = d.h_rowptr[i]; k < d.h_rowptr[i + 1]; ++k) {
+      const int c = d.h_col[k];
+      if (c != i) acc += hess[d.h_perm[k]] * x[c];                                                   // cols > i
+    }
+    for (int k = d.j_colptr[i]; k < d.j_colptr[i + 1]; ++k) acc += jac[k] * x[d.nw + d.j_row[k]];     // J' y
+  } else {
+    const int r = i - d.nw;
+    acc = bt.neg_d[(size_t)p * d.ng + r] * x[i];
+    for (int k = d.j_rowptr[r]; k < d.j_rowptr[r + 1]; ++k) acc += jac[d.j_perm[k]] * x[d.j_col[k]];
+  }
+  out[(size_t)p * nk + i] = acc;
+}

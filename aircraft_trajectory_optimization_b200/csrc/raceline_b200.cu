@@ -23,6 +23,7 @@
 #include "rk4_cells.cuh"
 #include "colloc_cells.cuh"
 #include "simple_rows.cuh"
+#include "kkt_blocks.cuh"
 
 namespace {
 
@@ -486,3 +487,5 @@ int rb_nlp_eval_all(const rb_problem* p, int B, const double* x, const double* v
 }
 
 }  // extern "C"
+
+#include "kkt_host.inc"

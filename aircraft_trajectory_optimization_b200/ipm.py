@@ -1,0 +1,463 @@
+'''
+Batched primal-dual interior-point driver (the `nlpsol('solver', 'ipopt', ...)` replacement).
+
+The reference hands its NLP to IPOPT through CasADi (drone3d/raceline/base_raceline.py:752-799)
+and calls `self.solver(x0=, lbx=, ubx=, lbg=, ubg=)` (:160-165).  This module is the same kind of
+solver -- a filter line-search barrier method following Waechter & Biegler (Math. Prog. 106, 2006),
+the algorithm IPOPT implements [third party, not in the reference tree] -- written so that B
+independent problem instances of one structure advance in lock step:
+
+    min f(x)   s.t.  lbg <= g(x) <= ubg,   lbx <= x <= ubx
+
+  * equality rows (lbg == ubg) stay equalities, inequality rows get slacks s with bounds;
+  * every iteration evaluates f, grad f, g, jac_g, hess_l for the whole batch (one launch of the
+    interval-cell kernel), condenses the slacks, and solves the KKT system with the batched
+    block-tridiagonal + border kernel (csrc/kkt_blocks.cuh) followed by iterative refinement;
+  * the block solver pivots symmetrically (Bunch-Parlett), so it reports the inertia of the KKT
+    matrix; a wrong inertia (not exactly ng negative eigenvalues) or a vanishing pivot triggers
+    IPOPT's delta_w / delta_c escalation schedule (Algorithm IC of the paper);
+  * monotone barrier update, fraction-to-the-boundary rule, filter with switching / Armijo
+    conditions; no restoration phase (a failed line search resets the filter and takes the
+    shortest trial step; three failures in a row mark the instance as failed).
+
+All state lives in torch tensors on the device of the inputs; the two heavy operations come from a
+*backend* object (`eval`, `kkt_solve`, `kkt_matvec`).  The product backend is `CudaBackend`
+(functions.NlpFunctions + kkt.KktSolver); there is no CPU backend in this package.
+'''
+from dataclasses import dataclass, field
+import time
+
+import numpy as np
+import torch
+
+
+@dataclass
+class IpmOptions:
+    tol: float = 1e-8
+    acceptable_tol: float = 1e-6
+    acceptable_iter: int = 15
+    max_iter: int = 1000
+    mu_init: float = 0.1
+    mu_min_factor: float = 0.1         # mu >= tol * mu_min_factor
+    kappa_eps: float = 10.0
+    kappa_mu: float = 0.2
+    theta_mu: float = 1.5
+    tau_min: float = 0.99
+    s_max: float = 100.0
+    kappa_sigma: float = 1e10
+    bound_push: float = 1e-2
+    bound_frac: float = 1e-2
+    bound_relax: float = 1e-8
+    kappa_d: float = 1e-4
+    gamma_theta: float = 1e-5
+    gamma_phi: float = 1e-8
+    delta_ls: float = 1.0
+    s_theta: float = 1.1
+    s_phi: float = 2.3
+    eta_phi: float = 1e-8
+    max_ls: int = 30
+    filter_size: int = 64
+    delta_w_first: float = 1e-4
+    delta_w_min: float = 1e-20
+    delta_w_max: float = 1e40
+    kappa_w_minus: float = 1.0 / 3.0
+    kappa_w_plus: float = 8.0
+    kappa_w_plus_first: float = 100.0
+    delta_c_bar: float = 1e-8
+    kappa_c: float = 0.25
+    refine_steps: int = 2
+    verbose: bool = False
+
+
+@dataclass
+class IpmResult:
+    x: torch.Tensor
+    f: torch.Tensor
+    g: torch.Tensor
+    lam_g: torch.Tensor
+    lam_x: torch.Tensor
+    success: torch.Tensor          # bool [B]
+    status: torch.Tensor           # int [B]: 0 optimal, 1 acceptable, 2 max_iter, 3 failed
+    iterations: torch.Tensor       # int [B]
+    kkt_error: torch.Tensor
+    n_iter: int = 0
+    n_eval: int = 0
+    n_factor: int = 0
+    t_eval: float = 0.0
+    t_kkt: float = 0.0
+    t_total: float = 0.0
+    history: list = field(default_factory=list)
+
+
+def _inf_norm(t):
+    return t.abs().amax(dim=1) if t.shape[1] else torch.zeros(t.shape[0], dtype=t.dtype, device=t.device)
+
+
+class InteriorPoint:
+    def __init__(self, backend, options: IpmOptions = None):
+        self.be = backend
+        self.opt = options or IpmOptions()
+
+    # ------------------------------------------------------------------------------------------------
+    def solve(self, x0, lbx, ubx, lbg, ubg, lam_g0=None) -> IpmResult:
+        o, be = self.opt, self.be
+        t_start = time.perf_counter()
+        dev, dt = x0.device, torch.float64
+        B, n = x0.shape
+        m = be.ng
+        exp = lambda a: torch.as_tensor(a, dtype=dt, device=dev).expand(B, -1)
+        lbx, ubx, lbg, ubg = exp(lbx), exp(ubx), exp(lbg), exp(ubg)
+        eq = (lbg == ubg)
+        ineq = ~eq
+        # relaxed bounds (IPOPT bound_relax_factor)
+        relax = lambda b, sgn: b + sgn * o.bound_relax * torch.clamp(b.abs(), min=1.0)
+        hasL, hasU = torch.isfinite(lbx), torch.isfinite(ubx)
+        xL = torch.where(hasL, relax(lbx, -1.0), torch.zeros_like(lbx))
+        xU = torch.where(hasU, relax(ubx, +1.0), torch.zeros_like(ubx))
+        shasL, shasU = torch.isfinite(lbg) & ineq, torch.isfinite(ubg) & ineq
+        sL = torch.where(shasL, relax(lbg, -1.0), torch.zeros_like(lbg))
+        sU = torch.where(shasU, relax(ubg, +1.0), torch.zeros_like(ubg))
+        ceq = torch.where(eq, lbg, torch.zeros_like(lbg))
+        # damping only for one-sided bounds
+        dampL, dampU = (hasL & ~hasU).to(dt), (hasU & ~hasL).to(dt)
+        sdampL, sdampU = (shasL & ~shasU).to(dt), (shasU & ~shasL).to(dt)
+        fL, fU, sfL, sfU = hasL.to(dt), hasU.to(dt), shasL.to(dt), shasU.to(dt)
+        n_bounds = (fL + fU).sum(1) + (sfL + sfU).sum(1)
+
+        def push(v, L, U, hL, hU):
+            ''' move v strictly inside [L, U] (IPOPT bound_push / bound_frac) '''
+            span = torch.where(hL & hU, U - L, torch.full_like(v, float('inf')))
+            pL = torch.minimum(o.bound_push * torch.clamp(L.abs(), min=1.0), o.bound_frac * span)
+            pU = torch.minimum(o.bound_push * torch.clamp(U.abs(), min=1.0), o.bound_frac * span)
+            v = torch.where(hL, torch.maximum(v, L + pL), v)
+            v = torch.where(hU, torch.minimum(v, U - pU), v)
+            return v
+
+        x = push(x0.to(dt).clone(), xL, xU, hasL, hasU)
+        res = IpmResult(None, None, None, None, None, None, None, None, None)
+        ones_B = torch.ones(B, dtype=dt, device=dev)
+
+        def evaluate(xx, yy, derivs):
+            t0 = time.perf_counter()
+            out = be.eval(xx, yy, ones_B, derivs)
+            if dev.type == 'cuda':
+                torch.cuda.synchronize(dev)
+            res.t_eval += time.perf_counter() - t0
+            res.n_eval += 1
+            return out
+
+        y = torch.zeros(B, m, dtype=dt, device=dev) if lam_g0 is None else lam_g0.to(dt).clone()
+        ev = evaluate(x, y, True)
+        s = push(torch.where(ineq, ev['g'], ceq), sL, sU, shasL, shasU)
+        s = torch.where(ineq, s, ceq)
+        zL, zU = fL.clone(), fU.clone()
+        vL, vU = sfL.clone(), sfU.clone()
+        mu = torch.full((B,), o.mu_init, dtype=dt, device=dev)
+        zero_h = torch.zeros_like(ev['hess'])
+
+        def kkt(hess, jac, dxd, negd, rhs):
+            t0 = time.perf_counter()
+            sol, st = be.kkt_solve(hess, jac, dxd, negd, rhs, o.refine_steps)
+            if dev.type == 'cuda':
+                torch.cuda.synchronize(dev)
+            res.t_kkt += time.perf_counter() - t0
+            res.n_factor += 1
+            return sol, st
+
+        def jt_y(jac, yy):
+            vec = torch.cat([torch.zeros(B, n, dtype=dt, device=dev), yy], dim=1)
+            z = torch.zeros(B, n, dtype=dt, device=dev)
+            return be.kkt_matvec(zero_h, jac, z, torch.zeros(B, m, dtype=dt, device=dev), vec)[:, :n]
+
+        # ---- least-squares multiplier estimate (IPOPT 3.6 in the paper) ------------------------------
+        if lam_g0 is None:
+            rhs = torch.cat([-(ev['grad_f'] - zL + zU), torch.where(ineq, vL - vU, torch.zeros_like(s))], dim=1)
+            negd = torch.where(ineq, -torch.ones_like(s), torch.zeros_like(s))
+            sol, st = kkt(zero_h, ev['jac'], torch.ones(B, n, dtype=dt, device=dev), negd, rhs)
+            y0 = sol[:, n:]
+            ok = torch.isfinite(y0).all(1) & (_inf_norm(y0) <= 1e3) & (st[:, 0] == 0)
+            y = torch.where(ok[:, None], y0, torch.zeros_like(y0))
+            ev = evaluate(x, y, True)
+
+        def slacks(xx, ss):
+            return (xx - xL, xU - xx, ss - sL, sU - ss)
+
+        def barrier(fv, xx, ss, mu_):
+            dL, dU, eL, eU = slacks(xx, ss)
+            lg = lambda d_, f_: (torch.log(torch.where(f_ > 0, d_, torch.ones_like(d_))) * f_).sum(1)
+            phi = fv - mu_ * (lg(dL, fL) + lg(dU, fU) + lg(eL, sfL) + lg(eU, sfU))
+            phi = phi + o.kappa_d * mu_ * ((dL * dampL).sum(1) + (dU * dampU).sum(1)
+                                          + (eL * sdampL).sum(1) + (eU * sdampU).sum(1))
+            return phi
+
+        def infeas(gv, ss):
+            return torch.where(eq, gv - ceq, gv - ss)
+
+        def errors(ev_, xx, ss, yy, zL_, zU_, vL_, vU_, mu_):
+            dL, dU, eL, eU = slacks(xx, ss)
+            gradL_x = ev_['grad_f'] + jt_y(ev_['jac'], yy) - zL_ + zU_
+            gradL_s = torch.where(ineq, -yy - vL_ + vU_, torch.zeros_like(yy))
+            c = infeas(ev_['g'], ss)
+            comp = torch.stack([_inf_norm((dL * zL_ - mu_[:, None]) * fL), _inf_norm((dU * zU_ - mu_[:, None]) * fU),
+                                _inf_norm((eL * vL_ - mu_[:, None]) * sfL), _inf_norm((eU * vU_ - mu_[:, None]) * sfU)]).amax(0)
+            zsum = (zL_ * fL + zU_ * fU).sum(1) + (vL_ * sfL + vU_ * sfU).sum(1)
+            n_tot = n + int(ineq[0].sum())
+            s_d = torch.clamp((yy.abs().sum(1) + zsum) / max(1, m + n_tot), min=o.s_max) / o.s_max
+            s_c = torch.clamp(zsum / torch.clamp(n_bounds, min=1.0), min=o.s_max) / o.s_max
+            dual = torch.maximum(_inf_norm(gradL_x), _inf_norm(gradL_s))
+            return torch.stack([dual / s_d, _inf_norm(c), comp / s_c]).amax(0), dual, _inf_norm(c), comp
+
+        # ---- state -------------------------------------------------------------------------------------
+        F = o.filter_size
+        filt_theta = torch.full((B, F), float('inf'), dtype=dt, device=dev)
+        filt_phi = torch.full((B, F), float('inf'), dtype=dt, device=dev)
+        filt_n = torch.zeros(B, dtype=torch.long, device=dev)
+        theta0 = infeas(ev['g'], s).abs().sum(1)
+        theta_max = 1e4 * torch.clamp(theta0, min=1.0)
+        theta_min = 1e-4 * torch.clamp(theta0, min=1.0)
+        filt_theta[:, 0] = theta_max          # the initial filter {theta >= theta_max}
+        filt_phi[:, 0] = -float('inf')
+        filt_n[:] = 1
+        delta_w_last = torch.zeros(B, dtype=dt, device=dev)
+        status = torch.full((B,), -1, dtype=torch.long, device=dev)
+        iters = torch.zeros(B, dtype=torch.long, device=dev)
+        acc_count = torch.zeros(B, dtype=torch.long, device=dev)
+        ls_fail = torch.zeros(B, dtype=torch.long, device=dev)
+        mu_floor = o.tol * o.mu_min_factor
+
+        def reset_filter(mask):
+            filt_theta[mask] = float('inf')
+            filt_phi[mask] = float('inf')
+            filt_theta[mask, 0] = theta_max[mask]
+            filt_phi[mask, 0] = -float('inf')
+            filt_n[mask] = 1
+
+        it = 0
+        while True:
+            active = status < 0
+            # ---- convergence and barrier update --------------------------------------------------------
+            E0, dual0, prim0, comp0 = errors(ev, x, s, y, zL, zU, vL, vU, torch.zeros_like(mu))
+            done = active & (E0 <= o.tol)
+            status[done] = 0
+            acc = active & ~done & (E0 <= o.acceptable_tol)
+            acc_count = torch.where(acc, acc_count + 1, torch.zeros_like(acc_count))
+            done_acc = acc & (acc_count >= o.acceptable_iter)
+            status[done_acc] = 1
+            active = status < 0
+            if o.verbose:
+                k = 0
+                print(f'{it:4d} f={float(ev["f"][k]):.8e} inf_pr={float(prim0[k]):.2e} inf_du={float(dual0[k]):.2e} '
+                      f'compl={float(comp0[k]):.2e} lg(mu)={np.log10(float(mu[k])):.1f} dw={float(delta_w_last[k]):.1e} '
+                      f'active={int(active.sum())}')
+            res.history.append((it, int(active.sum())))
+            if not bool(active.any()) or it >= o.max_iter:
+                break
+            for _ in range(4):
+                Emu = errors(ev, x, s, y, zL, zU, vL, vU, mu)[0]
+                upd = active & (Emu <= o.kappa_eps * mu) & (mu > mu_floor)
+                if not bool(upd.any()):
+                    break
+                mu_new = torch.clamp(torch.minimum(o.kappa_mu * mu, mu ** o.theta_mu), min=mu_floor)
+                mu = torch.where(upd, mu_new, mu)
+                reset_filter(upd)
+            tau = torch.clamp(1.0 - mu, min=o.tau_min)
+
+            # ---- the Newton system ---------------------------------------------------------------------
+            dL, dU, eL, eU = slacks(x, s)
+            inv = lambda d_, f_: f_ / torch.where(f_ > 0, d_, torch.ones_like(d_))
+            iL, iU, jL, jU = inv(dL, fL), inv(dU, fU), inv(eL, sfL), inv(eU, sfU)
+            Sx = zL * iL + zU * iU
+            Ss = vL * jL + vU * jU
+            mu_c = mu[:, None]
+            gphi_x = ev['grad_f'] - mu_c * iL + mu_c * iU + o.kappa_d * mu_c * (dampL - dampU)
+            gphi_s = torch.where(ineq, -mu_c * jL + mu_c * jU + o.kappa_d * mu_c * (sdampL - sdampU),
+                                 torch.zeros_like(s))
+            r_x = gphi_x + jt_y(ev['jac'], y)
+            r_s = torch.where(ineq, gphi_s - y, torch.zeros_like(s))
+            c = infeas(ev['g'], s)
+
+            delta_w = torch.zeros(B, dtype=dt, device=dev)
+            delta_c = torch.zeros(B, dtype=dt, device=dev)
+            need = active.clone()
+            dx = torch.zeros_like(x)
+            ds = torch.zeros_like(s)
+            dy = torch.zeros_like(y)
+            first_try = torch.ones(B, dtype=torch.bool, device=dev)
+            for attempt in range(40):
+                dw_c = delta_w[:, None]
+                Ss_reg = torch.where(ineq, Ss + dw_c, torch.ones_like(Ss))
+                negd = torch.where(ineq, -1.0 / Ss_reg, torch.zeros_like(Ss)) - delta_c[:, None]
+                rhs = torch.cat([-r_x, torch.where(ineq, -c - r_s / Ss_reg, -c)], dim=1)
+                sol, st = kkt(ev['hess'], ev['jac'], Sx + dw_c, negd, rhs)
+                dx_t, dy_t = sol[:, :n], sol[:, n:]
+                ds_t = torch.where(ineq, (dy_t - r_s) / Ss_reg, torch.zeros_like(s))
+                finite = torch.isfinite(sol).all(1)
+                singular = (st[:, 0] != 0) | ~finite
+                wrong_inertia = st[:, 1] != m
+                bad = need & (singular | wrong_inertia)
+                good = need & ~bad
+                dx = torch.where(good[:, None], dx_t, dx)
+                dy = torch.where(good[:, None], dy_t, dy)
+                ds = torch.where(good[:, None], ds_t, ds)
+                delta_w_last = torch.where(good & (delta_w > 0), delta_w, delta_w_last)
+                need = bad
+                if not bool(need.any()):
+                    break
+                # IPOPT's escalation schedule for delta_w (Algorithm IC)
+                start = torch.where(delta_w_last == 0, torch.full_like(delta_w, o.delta_w_first),
+                                    torch.clamp(o.kappa_w_minus * delta_w_last, min=o.delta_w_min))
+                grow = torch.where(delta_w_last == 0, o.kappa_w_plus_first * delta_w, o.kappa_w_plus * delta_w)
+                delta_w = torch.where(need, torch.where(first_try, start, grow), delta_w)
+                delta_c = torch.where(need & singular, o.delta_c_bar * mu ** o.kappa_c, delta_c)
+                first_try = first_try & ~need
+                hopeless = need & (delta_w > o.delta_w_max)
+                status[hopeless] = 3
+                need = need & ~hopeless
+                if not bool(need.any()):
+                    break
+            active = status < 0
+            am = active[:, None]
+            dx, ds, dy = dx * am, ds * am, dy * am
+
+            dzL = (mu_c * iL - zL - zL * iL * dx) * fL
+            dzU = (mu_c * iU - zU + zU * iU * dx) * fU
+            dvL = (mu_c * jL - vL - vL * jL * ds) * sfL
+            dvU = (mu_c * jU - vU + vU * jU * ds) * sfU
+
+            def max_step(d_, step, f_, t_):
+                ''' largest alpha in (0, 1] with d_ + alpha * step >= (1 - tau) d_ '''
+                ratio = torch.where((step < 0) & (f_ > 0), -t_[:, None] * d_ / step, torch.full_like(d_, float('inf')))
+                return torch.clamp(ratio.amin(1), max=1.0) if ratio.shape[1] else torch.ones_like(t_)
+
+            a_pr = torch.stack([max_step(dL, dx, fL, tau), max_step(dU, -dx, fU, tau),
+                                max_step(eL, ds, sfL, tau), max_step(eU, -ds, sfU, tau)]).amin(0)
+            a_du = torch.stack([max_step(zL, dzL, fL, tau), max_step(zU, dzU, fU, tau),
+                                max_step(vL, dvL, sfL, tau), max_step(vU, dvU, sfU, tau)]).amin(0)
+
+            # ---- filter line search ---------------------------------------------------------------------
+            theta = c.abs().sum(1)
+            phi = barrier(ev['f'], x, s, mu)
+            dphi = (gphi_x * dx).sum(1) + (gphi_s * ds).sum(1)
+            alpha = a_pr.clone()
+            searching = active.clone()
+            accepted_alpha = torch.zeros_like(alpha)
+            augment = torch.zeros(B, dtype=torch.bool, device=dev)
+            switch_base = (dphi < 0) & (theta <= theta_min)
+            last_alpha = alpha.clone()
+            for ls in range(o.max_ls):
+                xt = x + alpha[:, None] * dx
+                st_ = torch.where(ineq, s + alpha[:, None] * ds, ceq)
+                evt = evaluate(xt, y, False)
+                th_t = infeas(evt['g'], st_).abs().sum(1)
+                ph_t = barrier(evt['f'], xt, st_, mu)
+                okfin = torch.isfinite(th_t) & torch.isfinite(ph_t)
+                in_filter = ((th_t[:, None] >= (1 - o.gamma_theta) * filt_theta)
+                             & (ph_t[:, None] >= filt_phi - o.gamma_phi * filt_theta)).any(1)
+                sw = switch_base & (alpha * (-dphi).clamp(min=0) ** o.s_phi > o.delta_ls * theta ** o.s_theta)
+                armijo = ph_t <= phi + o.eta_phi * alpha * dphi
+                suff = (th_t <= (1 - o.gamma_theta) * theta) | (ph_t <= phi - o.gamma_phi * theta)
+                ok = okfin & ~in_filter & (th_t <= theta_max) & torch.where(sw, armijo, suff)
+                acc_now = searching & ok
+                accepted_alpha = torch.where(acc_now, alpha, accepted_alpha)
+                augment = torch.where(acc_now, ~(sw & armijo), augment)
+                searching = searching & ~ok
+                last_alpha = torch.where(searching, alpha, last_alpha)
+                if not bool(searching.any()):
+                    break
+                alpha = torch.where(searching, 0.5 * alpha, alpha)
+            # failed searches: reset the filter and take the shortest trial step
+            failed = searching
+            if bool(failed.any()):
+                ls_fail = torch.where(failed, ls_fail + 1, ls_fail)
+                reset_filter(failed)
+                accepted_alpha = torch.where(failed, last_alpha, accepted_alpha)
+                augment = augment & ~failed
+                status[failed & (ls_fail >= 3)] = 3
+            ls_fail = torch.where(active & ~failed, torch.zeros_like(ls_fail), ls_fail)
+
+            # ---- filter augmentation, step, multiplier reset ----------------------------------------------
+            if bool(augment.any()):
+                idx = torch.clamp(filt_n, max=F - 1)
+                rows = torch.nonzero(augment).squeeze(1)
+                filt_theta[rows, idx[rows]] = ((1 - o.gamma_theta) * theta)[rows]
+                filt_phi[rows, idx[rows]] = (phi - o.gamma_phi * theta)[rows]
+                filt_n[rows] = torch.clamp(filt_n[rows] + 1, max=F - 1)
+            a = accepted_alpha[:, None]
+            x = x + a * dx
+            s = torch.where(ineq, s + a * ds, ceq)
+            y = y + a * dy
+            ad = (a_du * active)[:, None]
+            zL, zU, vL, vU = zL + ad * dzL, zU + ad * dzU, vL + ad * dvL, vU + ad * dvU
+            dL, dU, eL, eU = slacks(x, s)
+
+            def reset(z_, d_, f_):
+                d_ = torch.where(f_ > 0, d_, torch.ones_like(d_))
+                lo, hi = mu_c / (o.kappa_sigma * d_), o.kappa_sigma * mu_c / d_
+                return torch.where(f_ > 0, torch.maximum(torch.minimum(z_, hi), lo), z_)
+
+            zL, zU, vL, vU = reset(zL, dL, fL), reset(zU, dU, fU), reset(vL, eL, sfL), reset(vU, eU, sfU)
+            iters = iters + active.long()
+            it += 1
+            if o.verbose:
+                print(f'      alpha_pr={float(accepted_alpha[0]):.3e} a_max={float(a_pr[0]):.3e} alpha_du={float(a_du[0]):.3e} '
+                      f'ls={ls + 1} failed={bool(failed[0])} theta={float(theta[0]):.3e} dphi={float(dphi[0]):.3e} '
+                      f'|dx|={float(dx[0].abs().max()):.2e} |dy|={float(dy[0].abs().max()):.2e} attempts={attempt + 1}')
+            ev = evaluate(x, y, True)
+
+        status[status < 0] = 2
+        E0 = errors(ev, x, s, y, zL, zU, vL, vU, torch.zeros_like(mu))[0]
+        res.x, res.f, res.g, res.lam_g = x, ev['f'], ev['g'], y
+        res.lam_x = zU - zL
+        res.status, res.success, res.iterations, res.kkt_error = status, status <= 1, iters, E0
+        res.n_iter = it
+        res.t_total = time.perf_counter() - t_start
+        return res
+
+
+class CudaBackend:
+    ''' eval through rb_eval_batch, KKT through rb_kkt_* (device tensors only) '''
+
+    def __init__(self, functions, vp, kkt_solver=None):
+        from .kkt import KktSolver
+        self.F = functions
+        self.st = functions.st
+        self.ng = self.st.ng
+        self.vp = vp                                   # device tensor (nvp,) or (B, nvp)
+        self.K = kkt_solver or KktSolver(self.st)
+        self._buf = {}
+
+    def _out(self, name, shape, dev):
+        t = self._buf.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.device != dev:
+            t = torch.empty(shape, dtype=torch.float64, device=dev)
+            self._buf[name] = t
+        return t
+
+    def eval(self, x, lam_g, lam_f, derivs):
+        st, dev, B = self.st, x.device, x.shape[0]
+        x = x.contiguous()
+        f, g = self._out('f', (B,), dev), self._out('g', (B, st.ng), dev)
+        if derivs:
+            gf = torch.empty(B, st.nw, dtype=torch.float64, device=dev)
+            jac = torch.empty(B, st.nnz_jac, dtype=torch.float64, device=dev)
+            hess = torch.empty(B, st.nnz_hess, dtype=torch.float64, device=dev)
+            f, g = torch.empty(B, dtype=torch.float64, device=dev), torch.empty(B, st.ng, dtype=torch.float64, device=dev)
+            self._scratch = self.F.eval_device(x, lam_g.contiguous(), lam_f, self.vp, None, f, gf, g, jac, hess,
+                                               getattr(self, '_scratch', None))
+            return dict(f=f, grad_f=gf, g=g, jac=jac, hess=hess)
+        f, g = torch.empty(B, dtype=torch.float64, device=dev), torch.empty(B, st.ng, dtype=torch.float64, device=dev)
+        self._scratch = self.F.eval_device(x, None, None, self.vp, None, f, None, g, None, None,
+                                           getattr(self, '_scratch', None))
+        return dict(f=f, g=g)
+
+    def kkt_matvec(self, hess, jac, dx_diag, neg_d, vec):
+        return self.K.matvec(hess, jac, dx_diag.contiguous(), neg_d.contiguous(), vec.contiguous())
+
+    def kkt_solve(self, hess, jac, dx_diag, neg_d, rhs, refine_steps):
+        dx_diag, neg_d, rhs = dx_diag.contiguous(), neg_d.contiguous(), rhs.contiguous()
+        sol, status = self.K.factor_solve(hess, jac, dx_diag, neg_d, rhs)
+        sol = sol.clone()
+        for _ in range(refine_steps):
+            r = rhs - self.K.matvec(hess, jac, dx_diag, neg_d, sol)
+            sol = sol + self.K.resolve(hess, jac, dx_diag, neg_d, r)
+        return sol, status

@@ -1,0 +1,362 @@
+'''
+Block structure of the interior-point KKT system (host side of csrc/kkt_blocks.cuh).
+
+Every interior-point iteration solves (reference: inside IPOPT, reached through
+`self.solver(x0=..., ...)`, drone3d/raceline/base_raceline.py:160-165; the reference picks the
+sparse symmetric-indefinite solver MA97 / MUMPS at :765-787)
+
+        [ W + Sigma_x + delta_w I      J'   ] [dx]   [r_x]
+        [ J                           -D    ] [dy] = [r_g]
+
+with W the upper-triangular CCS values of hess_l, J the CCS values of jac_g, D >= 0 diagonal
+(slack elimination of inequality rows + delta_c).  The unknowns are regrouped by interval:
+
+  * variable i of w  -> block of its interval (H[n] and Z/U/dU[n, :] -> block n);
+  * row r of g       -> block of the LAST interval it touches (continuity n-1 -> n lives in block n,
+                        next to the variables Z[n,0], U[n,0] on which it is the identity);
+  * whatever breaks the chain goes to a dense *border*: the variables of the first node that the
+    loop-closure rows tie to the last interval (base_raceline.py:492-514, drone_raceline.py:47-104),
+    the phase-start step sizes of the global-frame equal-step rows (base_raceline.py:891-905), and
+    rows that only touch border variables.
+
+In that order the matrix is block-tridiagonal (N diagonal blocks S_n, couplings L_n between block
+n+1 and block n that only involve the *variables* of block n) plus the border.  The kernel factors
+it by a block forward sweep with dense, partially pivoted Gauss-Jordan inverses of the diagonal
+Schur complements, carries 1 + nb right-hand sides (the residual and the border columns), sweeps
+back, and finishes with the dense nb x nb border system.
+
+All tables are int32 and problem-independent; values are gathered from (hess, jac, dx_diag, neg_D)
+through `src` codes  kind << 28 | index   (kind 0 hess, 1 jac, 2 dx_diag, 3 neg_D).
+'''
+from dataclasses import dataclass
+
+import numpy as np
+
+K_HESS, K_JAC, K_DX, K_ND = 0, 1, 2, 3
+_SHIFT = 28
+
+
+def src_code(kind, idx):
+    idx = np.asarray(idx, dtype=np.int64)
+    assert (idx < (1 << _SHIFT)).all()
+    return ((kind << _SHIFT) | idx).astype(np.int32)
+
+
+@dataclass
+class KKTStructure:
+    nw: int
+    ng: int
+    N: int                  # number of diagonal blocks
+    nb: int                 # border size
+    bmax: int               # largest diagonal block
+    mmax: int               # most coupling rows (rows of block n+1 touched by block n)
+    qmax: int               # most coupling columns (variables of block n touched from block n+1)
+    blk_ptr: np.ndarray     # [N+2] into unk (block N = border)
+    unk: np.ndarray         # KKT index (i < nw variable, nw + r row) of every block-local unknown
+    nvar: np.ndarray        # [N+1] number of variables at the head of every block
+    # diagonal blocks: S[pos] = value(src); pos = r * bmax + c, both triangles listed
+    dA_ptr: np.ndarray
+    dA_src: np.ndarray
+    dA_pos: np.ndarray
+    # coupling L_n (compressed): rows cr (local in block n+1), columns cc (local in block n)
+    cr_ptr: np.ndarray
+    cr: np.ndarray
+    cc_ptr: np.ndarray
+    cc: np.ndarray
+    cL_ptr: np.ndarray
+    cL_src: np.ndarray
+    cL_pos: np.ndarray      # rr * qmax + cc (compressed indices)
+    # border columns: entry (local row in block n, border column j)
+    bE_ptr: np.ndarray
+    bE_src: np.ndarray
+    bE_row: np.ndarray
+    bE_col: np.ndarray
+    # border-border
+    bG_src: np.ndarray
+    bG_pos: np.ndarray      # r * nb + c, both triangles listed
+    # for tests / reference assembly: block id and local index of every KKT unknown
+    blk: np.ndarray
+    loc: np.ndarray
+
+    @property
+    def nk(self):
+        return self.nw + self.ng
+
+    @property
+    def nrhs(self):
+        return 1 + self.nb
+
+    def tables(self):
+        ''' the int32 arrays the C ABI takes, in rb_kkt_desc order '''
+        return dict(blk_ptr=self.blk_ptr, unk=self.unk, nvar=self.nvar,
+                    dA_ptr=self.dA_ptr, dA_src=self.dA_src, dA_pos=self.dA_pos,
+                    cr_ptr=self.cr_ptr, cr=self.cr, cc_ptr=self.cc_ptr, cc=self.cc,
+                    cL_ptr=self.cL_ptr, cL_src=self.cL_src, cL_pos=self.cL_pos,
+                    bE_ptr=self.bE_ptr, bE_src=self.bE_src, bE_row=self.bE_row, bE_col=self.bE_col,
+                    bG_src=self.bG_src, bG_pos=self.bG_pos)
+
+
+def _var_interval(st):
+    S, P, N = st.nz + 2 * st.nu, st.K + 1, st.N
+    iv = np.empty(st.nw, dtype=np.int64)
+    iv[:N] = np.arange(N)
+    iv[N:] = (np.arange(st.nw - N) // (P * S))
+    return iv
+
+
+def build_kkt_structure(st) -> KKTStructure:
+    ''' st: NLPStructure (structure.py) '''
+    nw, ng, N = st.nw, st.ng, st.N
+    iv = _var_interval(st)
+    jr = np.asarray(st.jac_row, dtype=np.int64)
+    jc = np.repeat(np.arange(nw), np.diff(st.jac_colind))
+    hr = np.asarray(st.hess_row, dtype=np.int64)
+    hc = np.repeat(np.arange(nw), np.diff(st.hess_colind))
+
+    # ---- border variables: iterate until every row / Hessian pair spans at most two adjacent intervals
+    border = np.zeros(nw, dtype=bool)
+    BIG = 10 ** 9
+    for _ in range(8):
+        ivm = np.where(border[jc], -1, iv[jc])
+        rmax = np.full(ng, -1, dtype=np.int64)
+        np.maximum.at(rmax, jr, ivm)
+        far = (~border[jc]) & (iv[jc] < rmax[jr] - 1)
+        hfar_lo = (~border[hr]) & (~border[hc]) & (np.abs(iv[hr] - iv[hc]) > 1)
+        if not far.any() and not hfar_lo.any():
+            break
+        border[jc[far]] = True
+        lo = np.where(iv[hr] < iv[hc], hr, hc)
+        border[lo[hfar_lo]] = True
+    else:
+        raise RuntimeError('could not arrange the KKT system into a block-tridiagonal chain + border')
+
+    # ---- block of every unknown ---------------------------------------------------------------------
+    blk = np.empty(nw + ng, dtype=np.int64)
+    blk[:nw] = np.where(border, N, iv)
+    ivm = np.where(border[jc], -1, iv[jc])
+    rmax = np.full(ng, -1, dtype=np.int64)
+    np.maximum.at(rmax, jr, ivm)
+    blk[nw:] = np.where(rmax < 0, N, rmax)
+
+    # local order inside a block: variables (ascending w index) then rows (ascending g index)
+    order = np.lexsort((np.arange(nw + ng), blk))
+    unk = order.astype(np.int32)
+    counts = np.bincount(blk, minlength=N + 1)
+    blk_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    loc = np.empty(nw + ng, dtype=np.int64)
+    loc[order] = np.arange(nw + ng) - blk_ptr[blk[order]]
+    nvar = np.bincount(blk[:nw], minlength=N + 1).astype(np.int32)
+    bmax = int(counts[:N].max())
+    nb = int(counts[N])
+
+    # ---- all KKT entries (i, j, src) in the lower+upper sense: list each unordered pair once ------
+    ei = np.concatenate([hr, nw + jr])
+    ej = np.concatenate([hc, jc])
+    es = np.concatenate([src_code(K_HESS, np.arange(len(hr))), src_code(K_JAC, np.arange(len(jr)))])
+    bi, bj = blk[ei], blk[ej]
+    li, lj = loc[ei], loc[ej]
+
+    in_chain = (bi < N) & (bj < N)
+    assert (np.abs(bi - bj)[in_chain] <= 1).all()
+
+    # diagonal blocks (both triangles; the diagonal once)
+    dmask = in_chain & (bi == bj)
+    d_b = bi[dmask]
+    d_r, d_c, d_s = li[dmask], lj[dmask], es[dmask]
+    off = d_r != d_c
+    dA_b = np.concatenate([d_b, d_b[off]])
+    dA_pos = np.concatenate([d_r * bmax + d_c, (d_c * bmax + d_r)[off]])
+    dA_src = np.concatenate([d_s, d_s[off]])
+    o = np.argsort(dA_b, kind='stable')
+    dA_b, dA_pos, dA_src = dA_b[o], dA_pos[o], dA_src[o]
+    dA_ptr = np.concatenate([[0], np.cumsum(np.bincount(dA_b, minlength=N))]).astype(np.int32)
+
+    # couplings: entry between block n (column side) and block n+1 (row side)
+    cmask = in_chain & (bi != bj)
+    c_hi_is_i = bi[cmask] > bj[cmask]
+    c_n = np.minimum(bi[cmask], bj[cmask])                       # the lower block
+    c_row = np.where(c_hi_is_i, li[cmask], lj[cmask])            # local index in block n+1
+    c_col = np.where(c_hi_is_i, lj[cmask], li[cmask])            # local index in block n
+    c_src = es[cmask]
+    col_unknown_is_var = np.where(c_hi_is_i, ej[cmask], ei[cmask]) < nw
+    assert col_unknown_is_var.all(), 'a row of block n couples to block n+1'
+    cr_list, cc_list, cL_pos, cL_src_l = [], [], [], []
+    cr_ptr, cc_ptr, cL_ptr = [0], [0], [0]
+    mmax = qmax = 0
+    o = np.argsort(c_n, kind='stable')
+    c_n, c_row, c_col, c_src = c_n[o], c_row[o], c_col[o], c_src[o]
+    starts = np.searchsorted(c_n, np.arange(N + 1))
+    per_block = []
+    for n in range(N):
+        a, b = starts[n], starts[n + 1]
+        rows_u, rr = np.unique(c_row[a:b], return_inverse=True)
+        cols_u, cc_ = np.unique(c_col[a:b], return_inverse=True)
+        per_block.append((rows_u, cols_u, rr, cc_, c_src[a:b]))
+        mmax, qmax = max(mmax, len(rows_u)), max(qmax, len(cols_u))
+    for rows_u, cols_u, rr, cc_, s in per_block:
+        cr_list.append(rows_u), cc_list.append(cols_u)
+        cL_pos.append(rr * qmax + cc_), cL_src_l.append(s)
+        cr_ptr.append(cr_ptr[-1] + len(rows_u)), cc_ptr.append(cc_ptr[-1] + len(cols_u))
+        cL_ptr.append(cL_ptr[-1] + len(s))
+    cat = lambda v, dt=np.int32: (np.concatenate(v) if len(v) else np.zeros(0)).astype(dt)
+
+    # border columns
+    emask = (bi == N) ^ (bj == N)
+    e_border_is_i = bi[emask] == N
+    e_n = np.where(e_border_is_i, bj[emask], bi[emask])
+    e_row = np.where(e_border_is_i, lj[emask], li[emask])
+    e_col = np.where(e_border_is_i, li[emask], lj[emask])
+    e_src = es[emask]
+    o = np.argsort(e_n, kind='stable')
+    e_n, e_row, e_col, e_src = e_n[o], e_row[o], e_col[o], e_src[o]
+    bE_ptr = np.concatenate([[0], np.cumsum(np.bincount(e_n, minlength=N))]).astype(np.int32)
+
+    gmask = (bi == N) & (bj == N)
+    g_r, g_c, g_s = li[gmask], lj[gmask], es[gmask]
+    off = g_r != g_c
+    bG_pos = np.concatenate([g_r * max(nb, 1) + g_c, (g_c * max(nb, 1) + g_r)[off]])
+    bG_src = np.concatenate([g_s, g_s[off]])
+
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    return KKTStructure(
+        nw=nw, ng=ng, N=N, nb=nb, bmax=bmax, mmax=mmax, qmax=qmax,
+        blk_ptr=blk_ptr, unk=unk, nvar=nvar,
+        dA_ptr=dA_ptr, dA_src=i32(dA_src), dA_pos=i32(dA_pos),
+        cr_ptr=i32(cr_ptr), cr=cat(cr_list), cc_ptr=i32(cc_ptr), cc=cat(cc_list),
+        cL_ptr=i32(cL_ptr), cL_src=cat(cL_src_l), cL_pos=cat(cL_pos),
+        bE_ptr=bE_ptr, bE_src=i32(e_src), bE_row=i32(e_row), bE_col=i32(e_col),
+        bG_src=i32(bG_src), bG_pos=i32(bG_pos), blk=blk, loc=loc)
+
+
+# ---------------------------------------------------------------------------------------------------
+# ctypes binding (device tensors in, device tensors out; no CPU fallback)
+import ctypes
+
+_i32p = ctypes.POINTER(ctypes.c_int32)
+_i64p = ctypes.POINTER(ctypes.c_int64)
+
+
+class _KktDesc(ctypes.Structure):
+    _fields_ = ([(k, ctypes.c_int) for k in ('nw', 'ng', 'N', 'nb', 'bmax', 'mmax', 'qmax', 'nnz_hess',
+                                            'nnz_jac', 'n_bG')]
+                + [(k, _i32p) for k in ('blk_ptr', 'unk', 'dA_ptr', 'dA_src', 'dA_pos', 'cr_ptr', 'cr',
+                                        'cc_ptr', 'cc', 'cL_ptr', 'cL_src', 'cL_pos', 'bE_ptr', 'bE_src',
+                                        'bE_row', 'bE_col', 'bG_src', 'bG_pos')]
+                + [(k, _i64p) for k in ('jac_colind', 'jac_row', 'hess_colind', 'hess_row')])
+
+
+def bind_kkt(lib):
+    vp = ctypes.c_void_p
+    lib.rb_kkt_create.argtypes = [ctypes.POINTER(_KktDesc), ctypes.POINTER(vp)]
+    lib.rb_kkt_destroy.argtypes = [vp]
+    lib.rb_kkt_destroy.restype = None
+    lib.rb_kkt_factor_bytes.argtypes = [vp, ctypes.c_int]
+    lib.rb_kkt_factor_bytes.restype = ctypes.c_size_t
+    lib.rb_kkt_factor_solve.argtypes = [vp, ctypes.c_int] + [vp] * 9
+    lib.rb_kkt_resolve.argtypes = [vp, ctypes.c_int] + [vp] * 8
+    lib.rb_kkt_matvec.argtypes = [vp, ctypes.c_int] + [vp] * 7
+
+
+class KktSolver:
+    '''
+    Batched KKT factor / solve on the GPU for one problem structure.  All arguments are torch CUDA
+    fp64 tensors (contiguous); see include/raceline_b200.h for shapes.
+    '''
+
+    def __init__(self, st, ks: KKTStructure = None):
+        from .functions import load_library, _check
+        self._check = _check
+        self.lib = load_library()
+        bind_kkt(self.lib)
+        self.st = st
+        self.ks = ks or build_kkt_structure(st)
+        ks = self.ks
+        self._keep = []
+        d = _KktDesc()
+        d.nw, d.ng, d.N, d.nb, d.bmax, d.mmax, d.qmax = ks.nw, ks.ng, ks.N, ks.nb, ks.bmax, ks.mmax, ks.qmax
+        d.nnz_hess, d.nnz_jac, d.n_bG = st.nnz_hess, st.nnz_jac, len(ks.bG_src)
+        for name, arr in ks.tables().items():
+            if name == 'nvar':
+                continue
+            a = np.ascontiguousarray(arr, dtype=np.int32)
+            self._keep.append(a)
+            setattr(d, name, a.ctypes.data_as(_i32p))
+        for name in ('jac_colind', 'jac_row', 'hess_colind', 'hess_row'):
+            a = np.ascontiguousarray(getattr(st, name), dtype=np.int64)
+            self._keep.append(a)
+            setattr(d, name, a.ctypes.data_as(_i64p))
+        self.handle = ctypes.c_void_p()
+        _check(self.lib.rb_kkt_create(ctypes.byref(d), ctypes.byref(self.handle)), 'rb_kkt_create')
+        self._factors = None
+        self._factors_B = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, 'handle', None) is not None and self.handle.value:
+                self.lib.rb_kkt_destroy(self.handle)
+                self.handle = ctypes.c_void_p()
+        except Exception:
+            pass
+
+    def _factor_buffer(self, B, device):
+        import torch
+        if self._factors is None or self._factors_B < B or self._factors.device != device:
+            self._factors = None
+            nbytes = self.lib.rb_kkt_factor_bytes(self.handle, B)
+            self._factors = torch.empty(nbytes // 8, dtype=torch.float64, device=device)
+            self._factors_B = B
+        return self._factors
+
+    @staticmethod
+    def _p(t):
+        return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+    def _args(self, hess, jac, dx_diag, neg_d):
+        import torch
+        for t in (hess, jac, dx_diag, neg_d):
+            assert t.is_cuda and t.is_contiguous() and t.dtype == torch.float64
+        B = hess.shape[0]
+        assert hess.shape == (B, self.st.nnz_hess) and jac.shape == (B, self.st.nnz_jac)
+        assert dx_diag.shape == (B, self.ks.nw) and neg_d.shape == (B, self.ks.ng)
+        return B
+
+    def factor_solve(self, hess, jac, dx_diag, neg_d, rhs, sol=None, status=None, stream=None):
+        import torch
+        B = self._args(hess, jac, dx_diag, neg_d)
+        if sol is None:
+            sol = torch.empty_like(rhs)
+        if status is None:
+            status = torch.zeros(B, 2, dtype=torch.int32, device=rhs.device)
+        fac = self._factor_buffer(B, rhs.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(rhs.device).cuda_stream
+        p = self._p
+        self._check(self.lib.rb_kkt_factor_solve(self.handle, B, p(hess), p(jac), p(dx_diag), p(neg_d), p(rhs),
+                                                 p(sol), p(fac), p(status), ctypes.c_void_p(stream)),
+                    'rb_kkt_factor_solve')
+        return sol, status
+
+    def resolve(self, hess, jac, dx_diag, neg_d, rhs, sol=None, stream=None):
+        import torch
+        B = self._args(hess, jac, dx_diag, neg_d)
+        if sol is None:
+            sol = torch.empty_like(rhs)
+        assert self._factors is not None and self._factors_B >= B, 'factor_solve first'
+        if stream is None:
+            stream = torch.cuda.current_stream(rhs.device).cuda_stream
+        p = self._p
+        self._check(self.lib.rb_kkt_resolve(self.handle, B, p(hess), p(jac), p(dx_diag), p(neg_d), p(rhs), p(sol),
+                                            p(self._factors), ctypes.c_void_p(stream)), 'rb_kkt_resolve')
+        return sol
+
+    def matvec(self, hess, jac, dx_diag, neg_d, vec, out=None, stream=None):
+        import torch
+        B = self._args(hess, jac, dx_diag, neg_d)
+        if out is None:
+            out = torch.empty_like(vec)
+        if stream is None:
+            stream = torch.cuda.current_stream(vec.device).cuda_stream
+        p = self._p
+        self._check(self.lib.rb_kkt_matvec(self.handle, B, p(hess), p(jac), p(dx_diag), p(neg_d), p(vec), p(out),
+                                           ctypes.c_void_p(stream)), 'rb_kkt_matvec')
+        return out

@@ -135,6 +135,45 @@ int rb_nlp_hess_l(const rb_problem* p, int B, const double* x, const double* vp,
 int rb_nlp_eval_all(const rb_problem* p, int B, const double* x, const double* vp, const double* lam_f,
                     const double* lam_g, double* f, double* grad_f, double* g, double* jac, double* hess);
 
+/* ---- KKT factor / solve of the interior-point step ---------------------------------------------
+ * Replaces the sparse symmetric-indefinite solve IPOPT performs on every iteration of
+ *     sol = self.solver(x0=..., lbx=..., ubx=..., lbg=..., ubg=...)   drone3d/raceline/base_raceline.py:160-165
+ * (linear solver MA97 / MUMPS selected at base_raceline.py:765-787) for the matrix
+ *     [ W + diag(dx_diag)   J'           ]      W = hess_l values (upper-triangular CCS), J = jac_g values (CCS)
+ *     [ J                   diag(neg_d)  ]
+ * The unknowns are grouped into interval blocks + a dense border by the host
+ * (aircraft_trajectory_optimization_b200/kkt.py documents every table).  All device pointers;
+ * asynchronous on `stream`. */
+typedef struct rb_kkt rb_kkt;
+
+typedef struct rb_kkt_desc {
+  int nw, ng, N, nb, bmax, mmax, qmax, nnz_hess, nnz_jac, n_bG;
+  const int32_t *blk_ptr, *unk;                           /* [N+2], [nw+ng] */
+  const int32_t *dA_ptr, *dA_src, *dA_pos;                /* diagonal blocks */
+  const int32_t *cr_ptr, *cr, *cc_ptr, *cc;               /* coupling rows / columns */
+  const int32_t *cL_ptr, *cL_src, *cL_pos;                /* coupling entries */
+  const int32_t *bE_ptr, *bE_src, *bE_row, *bE_col;       /* border columns */
+  const int32_t *bG_src, *bG_pos;                         /* border x border */
+  const int64_t *jac_colind, *jac_row, *hess_colind, *hess_row;   /* CCS patterns (for K v products) */
+} rb_kkt_desc;
+
+int rb_kkt_create(const rb_kkt_desc* desc, rb_kkt** out);
+void rb_kkt_destroy(rb_kkt* k);
+/* bytes of factor storage (block inverses, coupling solves, border columns) for a batch of B */
+size_t rb_kkt_factor_bytes(const rb_kkt* k, int B);
+/* factor K and solve K sol = rhs for B instances.  hess [B][nnz_hess], jac [B][nnz_jac], dx_diag [B][nw],
+ * neg_d [B][ng], rhs / sol [B][nw+ng] in (w, g) order; status [B][2] (optional): vanishing pivots met, and
+ * the number of negative eigenvalues of K (the interior-point driver expects exactly ng). */
+int rb_kkt_factor_solve(const rb_kkt* k, int B, const double* hess, const double* jac, const double* dx_diag,
+                        const double* neg_d, const double* rhs, double* sol, void* factors, int* status,
+                        void* stream);
+/* solve with the stored factors (the value arrays must be unchanged since rb_kkt_factor_solve) */
+int rb_kkt_resolve(const rb_kkt* k, int B, const double* hess, const double* jac, const double* dx_diag,
+                   const double* neg_d, const double* rhs, double* sol, void* factors, void* stream);
+/* out = K vec */
+int rb_kkt_matvec(const rb_kkt* k, int B, const double* hess, const double* jac, const double* dx_diag,
+                  const double* neg_d, const double* vec, double* out, void* stream);
+
 /* instrumentation: when enabled, every rb_eval_batch brackets the interval-cell kernel (the dominant
  * kernel) with CUDA events on the launching stream; rb_profile_cell_ms waits for them, returns the
  * summed duration and the number of bracketed launches, and resets the counters. */

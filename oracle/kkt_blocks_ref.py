@@ -1,0 +1,105 @@
+'''
+CPU checkers for the KKT solve.  TEST INFRASTRUCTURE ONLY (oracle/__init__.py).
+
+  * `kkt_matrix`   assembles the interior-point KKT matrix the way IPOPT hands it to its sparse
+                   symmetric solver [third party; selected at drone3d/raceline/base_raceline.py:765-787]:
+                   [[W + diag(dx_diag), J'], [J, -diag(D)]] from CCS values, as a scipy sparse matrix.
+  * `sparse_solve` solves it with scipy's SuperLU (the independent answer).
+  * `block_solve`  walks the product's block tables (aircraft_trajectory_optimization_b200/kkt.py)
+                   in numpy, step for step like csrc/kkt_blocks.cuh, so that table errors and kernel
+                   errors can be told apart.
+'''
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+
+def kkt_matrix(st, hess, jac, dx_diag, D):
+    nw, ng = st.nw, st.ng
+    W = sp.csc_matrix((hess, st.hess_row, st.hess_colind), shape=(nw, nw))
+    W = W + sp.triu(W, 1).T + sp.diags(dx_diag)
+    J = sp.csc_matrix((jac, st.jac_row, st.jac_colind), shape=(ng, nw))
+    return sp.bmat([[W, J.T], [J, -sp.diags(D)]], format='csc')
+
+
+def sparse_solve(st, hess, jac, dx_diag, D, rhs):
+    K = kkt_matrix(st, hess, jac, dx_diag, D)
+    return spla.splu(K).solve(rhs)
+
+
+def _gather(ks, src, hess, jac, dx_diag, neg_d):
+    kind = src >> 28
+    idx = src & ((1 << 28) - 1)
+    out = np.empty(len(src))
+    for k, arr in enumerate((hess, jac, dx_diag, neg_d)):
+        m = kind == k
+        out[m] = arr[idx[m]]
+    return out
+
+
+def block_solve(ks, hess, jac, dx_diag, D, rhs, with_inertia=False):
+    ''' ks: KKTStructure.  Returns the solution in the original (w, g) ordering (and, on request, the
+    number of negative eigenvalues summed over the block pivots, which equals that of K). '''
+    neg = 0
+    N, nb, bmax, qmax = ks.N, ks.nb, ks.bmax, ks.qmax
+    nw = ks.nw
+    neg_d = -np.asarray(D)
+    nrhs = 1 + nb
+    diag_of = lambda u: np.where(u < nw, dx_diag[np.minimum(u, nw - 1)], neg_d[np.maximum(u - nw, 0)])
+    Z = [None] * N
+    YL = [None] * N
+    carry = None
+    rcarry = None
+    for n in range(N):
+        u = ks.unk[ks.blk_ptr[n]:ks.blk_ptr[n + 1]]
+        b = len(u)
+        M = np.zeros((bmax, bmax))
+        a, e = ks.dA_ptr[n], ks.dA_ptr[n + 1]
+        M.ravel()[ks.dA_pos[a:e]] = _gather(ks, ks.dA_src[a:e], hess, jac, dx_diag, neg_d)
+        M[np.arange(b), np.arange(b)] += diag_of(u)
+        Y = np.zeros((b, nrhs))
+        Y[:, 0] = rhs[u]
+        a, e = ks.bE_ptr[n], ks.bE_ptr[n + 1]
+        Y[ks.bE_row[a:e], 1 + ks.bE_col[a:e]] = _gather(ks, ks.bE_src[a:e], hess, jac, dx_diag, neg_d)
+        if n > 0:
+            cr = ks.cr[ks.cr_ptr[n - 1]:ks.cr_ptr[n]]
+            M[np.ix_(cr, cr)] -= carry
+            Y[cr] -= rcarry
+        Sinv = np.linalg.inv(M[:b, :b])
+        neg += int((np.linalg.eigvalsh(M[:b, :b]) < 0).sum())
+        Z[n] = Sinv @ Y
+        if n < N - 1:
+            cc = ks.cc[ks.cc_ptr[n]:ks.cc_ptr[n + 1]]
+            m = ks.cr_ptr[n + 1] - ks.cr_ptr[n]
+            Lc = np.zeros((max(m, 1), qmax))
+            a, e = ks.cL_ptr[n], ks.cL_ptr[n + 1]
+            Lc.ravel()[ks.cL_pos[a:e]] = _gather(ks, ks.cL_src[a:e], hess, jac, dx_diag, neg_d)
+            Lc = Lc[:m, :len(cc)]
+            YL[n] = Sinv[:, cc] @ Lc.T              # b x m
+            carry = Lc @ YL[n][cc]                  # m x m
+            rcarry = Lc @ Z[n][cc]                  # m x nrhs
+    X = [None] * N
+    X[N - 1] = Z[N - 1]
+    for n in range(N - 2, -1, -1):
+        cr = ks.cr[ks.cr_ptr[n]:ks.cr_ptr[n + 1]]
+        X[n] = Z[n] - YL[n] @ X[n + 1][cr]
+    sol = np.zeros(ks.nk)
+    ub = ks.unk[ks.blk_ptr[N]:ks.blk_ptr[N + 1]]
+    if nb:
+        G = np.zeros((nb, nb))
+        G.ravel()[ks.bG_pos] = _gather(ks, ks.bG_src, hess, jac, dx_diag, neg_d)
+        G[np.arange(nb), np.arange(nb)] += diag_of(ub)
+        rb = rhs[ub].copy()
+        for n in range(N):
+            a, e = ks.bE_ptr[n], ks.bE_ptr[n + 1]
+            v = _gather(ks, ks.bE_src[a:e], hess, jac, dx_diag, neg_d)
+            # E' X: row j of E' picks entries (row l of block n, column j)
+            np.subtract.at(G, ks.bE_col[a:e], v[:, None] * X[n][ks.bE_row[a:e], 1:])
+            np.subtract.at(rb, ks.bE_col[a:e], v * X[n][ks.bE_row[a:e], 0])
+        xb = np.linalg.solve(G, rb)
+        neg += int((np.linalg.eigvalsh(G) < 0).sum())
+        sol[ub] = xb
+    for n in range(N):
+        u = ks.unk[ks.blk_ptr[n]:ks.blk_ptr[n + 1]]
+        sol[u] = X[n][:, 0] - (X[n][:, 1:] @ xb if nb else 0.0)
+    return (sol, neg) if with_inertia else sol
