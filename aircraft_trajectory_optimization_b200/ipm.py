@@ -289,6 +289,12 @@ class InteriorPoint:
                 negd = torch.where(ineq, -1.0 / Ss_reg, torch.zeros_like(Ss)) - delta_c[:, None]
                 rhs = torch.cat([-r_x, torch.where(ineq, -c - r_s / Ss_reg, -c)], dim=1)
                 sol, st = kkt(ev['hess'], ev['jac'], Sx + dw_c, negd, rhs)
+                if o.verbose and attempt >= 1:
+                    print(f'        attempt {attempt}: dw={float(delta_w[0]):.2e} dc={float(delta_c[0]):.2e} bad_piv={int(st[0, 0])} neg={int(st[0, 1])} (want {m})')
+                if attempt == 0 and it == int(__import__("os").environ.get("RB_IPM_DUMP_IT", "-1")):
+                    import os
+                    if os.environ.get('RB_IPM_DUMP'):
+                        torch.save(dict(hess=ev['hess'], jac=ev['jac'], Sx=Sx, Ss=Ss, ineq=ineq, x=x, y=y), os.environ['RB_IPM_DUMP'])
                 dx_t, dy_t = sol[:, :n], sol[:, n:]
                 ds_t = torch.where(ineq, (dy_t - r_s) / Ss_reg, torch.zeros_like(s))
                 finite = torch.isfinite(sol).all(1)
@@ -303,13 +309,17 @@ class InteriorPoint:
                 need = bad
                 if not bool(need.any()):
                     break
+                # too few negative eigenvalues or a vanishing pivot: the constraint Jacobian is (numerically)
+                # rank deficient -> perturb the constraint block first and retry with the same delta_w
+                degenerate = need & (singular | (st[:, 1] < m)) & (delta_c == 0)
+                delta_c = torch.where(degenerate, o.delta_c_bar * mu ** o.kappa_c, delta_c)
+                esc = need & ~degenerate
                 # IPOPT's escalation schedule for delta_w (Algorithm IC)
                 start = torch.where(delta_w_last == 0, torch.full_like(delta_w, o.delta_w_first),
                                     torch.clamp(o.kappa_w_minus * delta_w_last, min=o.delta_w_min))
                 grow = torch.where(delta_w_last == 0, o.kappa_w_plus_first * delta_w, o.kappa_w_plus * delta_w)
-                delta_w = torch.where(need, torch.where(first_try, start, grow), delta_w)
-                delta_c = torch.where(need & singular, o.delta_c_bar * mu ** o.kappa_c, delta_c)
-                first_try = first_try & ~need
+                delta_w = torch.where(esc, torch.where(first_try, start, grow), delta_w)
+                first_try = first_try & ~esc
                 hopeless = need & (delta_w > o.delta_w_max)
                 status[hopeless] = 3
                 need = need & ~hopeless

@@ -11,16 +11,20 @@ sparse symmetric-indefinite solver MA97 / MUMPS at :765-787)
 with W the upper-triangular CCS values of hess_l, J the CCS values of jac_g, D >= 0 diagonal
 (slack elimination of inequality rows + delta_c).  The unknowns are regrouped by interval:
 
-  * variable i of w  -> block of its interval (H[n] and Z/U/dU[n, :] -> block n);
-  * row r of g       -> block of the LAST interval it touches (continuity n-1 -> n lives in block n,
-                        next to the variables Z[n,0], U[n,0] on which it is the identity);
-  * whatever breaks the chain goes to a dense *border*: the variables of the first node that the
-    loop-closure rows tie to the last interval (base_raceline.py:492-514, drone_raceline.py:47-104),
-    the phase-start step sizes of the global-frame equal-step rows (base_raceline.py:891-905), and
-    rows that only touch border variables.
+  * stage triple n = [c_{n-1}, x_n; rows] with x_n = (Z[n,0], U[n,0]) the node variables, c_{n-1} =
+    (H[n-1], dU[n-1,0], interior collocation points of interval n-1) the variables that produce x_n,
+    and every row that is the identity on x_n (continuity / shooting rows n-1 -> n, which stay full
+    rank inside the triple even through the quaternion renormalisation) or only touches the triple;
+  * the triples are swept from n = N-1 down to 1: a Riccati-type recursion whose pivots are the
+    stage-wise reduced Hessians (eliminating c_n together with its own node x_n, or the rows with the
+    interval they leave instead of the node they define, makes the diagonal blocks singular or
+    ill-conditioned -- both were tried);
+  * the loop closes through triple 0 = [c_{N-1}, x_0; closure rows] (base_raceline.py:492-514,
+    drone_raceline.py:47-104), which forms the dense *border* together with the phase-start step
+    sizes of the global-frame equal-step rows (base_raceline.py:891-905).
 
-In that order the matrix is block-tridiagonal (N diagonal blocks S_n, couplings L_n between block
-n+1 and block n that only involve the *variables* of block n) plus the border.  The kernel factors
+In that order the matrix is block-tridiagonal (N-1 diagonal blocks S_n, couplings L_n between
+consecutive triples) plus the border.  The kernel factors
 it by a block forward sweep with dense, partially pivoted Gauss-Jordan inverses of the diagonal
 Schur complements, carries 1 + nb right-hand sides (the residual and the border columns), sweeps
 back, and finishes with the dense nb x nb border system.
@@ -96,47 +100,105 @@ class KKTStructure:
                     bG_src=self.bG_src, bG_pos=self.bG_pos)
 
 
-def _var_interval(st):
+def _var_stage(st):
+    '''
+    stage triple of every variable: node variables x_n = (Z[n,0], U[n,0]) belong to triple n, everything
+    else of interval n (H[n], dU[n,0] and the interior collocation points) is c_n and belongs to triple
+    n + 1 -- next to the node x_{n+1} it produces.  Returns (triple, is_node).
+    '''
     S, P, N = st.nz + 2 * st.nu, st.K + 1, st.N
-    iv = np.empty(st.nw, dtype=np.int64)
-    iv[:N] = np.arange(N)
-    iv[N:] = (np.arange(st.nw - N) // (P * S))
-    return iv
+    i = np.arange(st.nw - N)
+    n = i // (P * S)
+    k = (i % (P * S)) // S
+    j = i % S
+    node = (k == 0) & (j < st.nz + st.nu)
+    t = np.empty(st.nw, dtype=np.int64)
+    t[:N] = np.arange(N) + 1
+    t[N:] = np.where(node, n, n + 1)
+    is_node = np.zeros(st.nw, dtype=bool)
+    is_node[N:] = node
+    return t, is_node
 
 
 def build_kkt_structure(st) -> KKTStructure:
     ''' st: NLPStructure (structure.py) '''
     nw, ng, N = st.nw, st.ng, st.N
-    iv = _var_interval(st)
+    t, is_node = _var_stage(st)
     jr = np.asarray(st.jac_row, dtype=np.int64)
     jc = np.repeat(np.arange(nw), np.diff(st.jac_colind))
     hr = np.asarray(st.hess_row, dtype=np.int64)
     hc = np.repeat(np.arange(nw), np.diff(st.hess_colind))
 
-    # ---- border variables: iterate until every row / Hessian pair spans at most two adjacent intervals
-    border = np.zeros(nw, dtype=bool)
-    BIG = 10 ** 9
+    # ---- stage triples and border ---------------------------------------------------------------------
+    # Triple n = [c_{n-1}, x_n; rows that are the identity on x_n].  The loop closes through triple 0 =
+    # triple N = [c_{N-1}, x_0; closure rows], which becomes the border: x_0 is `low` (it couples to
+    # triple 1 like any x_{n-1} does), c_{N-1} is `high` (anything touching it is a border row).
+    LOW, HIGH = -1, N
+    tt = t.copy()
+    tt[(t == 0)] = LOW
+    tt[(t == N)] = HIGH
+    # far couplings that are not part of the loop (the equal-step star rows of the global frame): the
+    # variable at the low end of several far rows moves to the border as a `low` variable
     for _ in range(8):
-        ivm = np.where(border[jc], -1, iv[jc])
-        rmax = np.full(ng, -1, dtype=np.int64)
-        np.maximum.at(rmax, jr, ivm)
-        far = (~border[jc]) & (iv[jc] < rmax[jr] - 1)
-        hfar_lo = (~border[hr]) & (~border[hc]) & (np.abs(iv[hr] - iv[hc]) > 1)
-        if not far.any() and not hfar_lo.any():
+        rmax = np.full(ng, LOW, dtype=np.int64)
+        np.maximum.at(rmax, jr, tt[jc])
+        far = (tt[jc] != LOW) & (tt[jc] < rmax[jr] - 1)
+        hfar = (tt[hr] != LOW) & (tt[hc] != LOW) & (np.abs(tt[hr] - tt[hc]) > 1)
+        if not far.any() and not hfar.any():
             break
-        border[jc[far]] = True
-        lo = np.where(iv[hr] < iv[hc], hr, hc)
-        border[lo[hfar_lo]] = True
+        tt[jc[far]] = LOW
+        lo = np.where(tt[hr] < tt[hc], hr, hc)
+        tt[lo[hfar]] = LOW
     else:
         raise RuntimeError('could not arrange the KKT system into a block-tridiagonal chain + border')
+    rmax = np.full(ng, LOW, dtype=np.int64)
+    np.maximum.at(rmax, jr, tt[jc])
+    row_t = np.where(rmax == LOW, HIGH, rmax)
 
-    # ---- block of every unknown ---------------------------------------------------------------------
+    # chain blocks are the triples N-1, N-2, ..., 1 in that order (the sweep runs backward in time: a
+    # Riccati recursion); block index Nc = N - 1 is the border
+    Nc = N - 1
+    to_chain = lambda tv: np.where((tv == LOW) | (tv == HIGH), Nc, Nc - tv)
     blk = np.empty(nw + ng, dtype=np.int64)
-    blk[:nw] = np.where(border, N, iv)
-    ivm = np.where(border[jc], -1, iv[jc])
-    rmax = np.full(ng, -1, dtype=np.int64)
-    np.maximum.at(rmax, jr, ivm)
-    blk[nw:] = np.where(rmax < 0, N, rmax)
+    blk[:nw] = to_chain(tt)
+    blk[nw:] = to_chain(row_t)
+    N = Nc
+
+    # ---- structural rank of the equality rows inside every triple -------------------------------------
+    # A triple must be able to satisfy its own equality rows with its own variables, otherwise its diagonal
+    # block is singular whatever the values (the axial gate equation of the global frame pins the node
+    # position, which the shooting rows and the equal-step row of that triple already determine).  Rows
+    # that are structurally dependent on the earlier rows of their triple -- tested with random values on
+    # the sparsity pattern -- move to the border.
+    eq_row = np.asarray(st.lbg) == np.asarray(st.ubg)
+    rng = np.random.default_rng(12345)
+    jval = rng.uniform(0.5, 1.5, len(jr)) * rng.choice([-1.0, 1.0], len(jr))
+    ent_ok = eq_row[jr] & (blk[nw + jr] < N) & (blk[jc] == blk[nw + jr])
+    order_e = np.lexsort((jr[ent_ok], blk[nw + jr][ent_ok]))
+    e_r, e_c, e_v, e_b = jr[ent_ok][order_e], jc[ent_ok][order_e], jval[ent_ok][order_e], blk[nw + jr][ent_ok][order_e]
+    bstart = np.searchsorted(e_b, np.arange(N + 1))
+    demoted = []
+    for n in range(N):
+        a, b = bstart[n], bstart[n + 1]
+        if a == b:
+            continue
+        rows_u, ri = np.unique(e_r[a:b], return_inverse=True)
+        cols_u, ci = np.unique(e_c[a:b], return_inverse=True)
+        A = np.zeros((len(rows_u), len(cols_u)))
+        A[ri, ci] = e_v[a:b]
+        Q = np.zeros((0, len(cols_u)))
+        for k in range(len(rows_u)):
+            r = A[k] - (Q.T @ (Q @ A[k]) if len(Q) else 0.0)
+            if np.linalg.norm(r) > 1e-8 * np.linalg.norm(A[k]):
+                Q = np.vstack([Q, r / np.linalg.norm(r)])
+            else:
+                demoted.append(rows_u[k])
+    # equality rows of a triple without any variable of that triple cannot be pivoted there either
+    has_own = np.zeros(ng, dtype=bool)
+    has_own[jr[blk[jc] == blk[nw + jr]]] = True
+    demoted += list(np.nonzero(eq_row & (blk[nw:] < N) & ~has_own)[0])
+    if demoted:
+        blk[nw + np.array(demoted, dtype=np.int64)] = N
 
     # local order inside a block: variables (ascending w index) then rows (ascending g index)
     order = np.lexsort((np.arange(nw + ng), blk))
@@ -178,8 +240,6 @@ def build_kkt_structure(st) -> KKTStructure:
     c_row = np.where(c_hi_is_i, li[cmask], lj[cmask])            # local index in block n+1
     c_col = np.where(c_hi_is_i, lj[cmask], li[cmask])            # local index in block n
     c_src = es[cmask]
-    col_unknown_is_var = np.where(c_hi_is_i, ej[cmask], ei[cmask]) < nw
-    assert col_unknown_is_var.all(), 'a row of block n couples to block n+1'
     cr_list, cc_list, cL_pos, cL_src_l = [], [], [], []
     cr_ptr, cc_ptr, cL_ptr = [0], [0], [0]
     mmax = qmax = 0

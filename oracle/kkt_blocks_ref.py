@@ -37,6 +37,56 @@ def _gather(ks, src, hess, jac, dx_diag, neg_d):
     return out
 
 
+def sym_invert_bp(A):
+    '''
+    inverse and number of negative eigenvalues of the symmetric matrix A by Gauss-Jordan sweeps with
+    Bunch-Parlett pivoting -- the numpy twin of kkt_sym_invert in csrc/kkt_blocks.cuh
+    '''
+    M = np.array(A, dtype=float)
+    b = M.shape[0]
+    alpha = 0.6403882032022076
+    unswept = np.ones(b, dtype=bool)
+    neg = 0
+    while unswept.any():
+        idx = np.nonzero(unswept)[0]
+        sub = np.abs(M[np.ix_(idx, idx)])
+        dg = np.diag(sub)
+        kd = idx[int(np.argmax(dg))]
+        vd = dg.max()
+        off = sub - np.diag(dg)
+        vo = off.max() if len(idx) > 1 else -1.0
+        if len(idx) == 1 or vd >= alpha * vo:
+            k = kd
+            d = M[k, k]
+            if not abs(d) > 1e-250:
+                d = 1e-250
+            neg += d < 0
+            col = M[:, k].copy()
+            row = M[k, :] / d
+            M -= np.outer(col, row)
+            M[k, :] = row
+            M[:, k] = -col / d
+            M[k, k] = 1.0 / d
+            unswept[k] = False
+        else:
+            io, jo = np.unravel_index(int(np.argmax(np.triu(off, 1))), off.shape)
+            p, q = idx[io], idx[jo]
+            E = M[np.ix_([p, q], [p, q])]
+            det = E[0, 0] * E[1, 1] - E[0, 1] ** 2
+            if not abs(det) > 1e-250:
+                det = -1e-250
+            neg += 1 if det < 0 else (2 if E[0, 0] + E[1, 1] < 0 else 0)
+            Ei = np.array([[E[1, 1], -E[0, 1]], [-E[0, 1], E[0, 0]]]) / det
+            cols = M[:, [p, q]].copy()
+            rows = Ei @ M[[p, q], :]
+            M -= cols @ rows
+            M[[p, q], :] = rows
+            M[:, [p, q]] = -cols @ Ei
+            M[np.ix_([p, q], [p, q])] = Ei
+            unswept[[p, q]] = False
+    return M, int(neg)
+
+
 def block_solve(ks, hess, jac, dx_diag, D, rhs, with_inertia=False):
     ''' ks: KKTStructure.  Returns the solution in the original (w, g) ordering (and, on request, the
     number of negative eigenvalues summed over the block pivots, which equals that of K). '''
@@ -65,8 +115,8 @@ def block_solve(ks, hess, jac, dx_diag, D, rhs, with_inertia=False):
             cr = ks.cr[ks.cr_ptr[n - 1]:ks.cr_ptr[n]]
             M[np.ix_(cr, cr)] -= carry
             Y[cr] -= rcarry
-        Sinv = np.linalg.inv(M[:b, :b])
-        neg += int((np.linalg.eigvalsh(M[:b, :b]) < 0).sum())
+        Sinv, ng_ = sym_invert_bp(M[:b, :b])
+        neg += ng_
         Z[n] = Sinv @ Y
         if n < N - 1:
             cc = ks.cc[ks.cc_ptr[n]:ks.cc_ptr[n + 1]]
@@ -96,8 +146,9 @@ def block_solve(ks, hess, jac, dx_diag, D, rhs, with_inertia=False):
             # E' X: row j of E' picks entries (row l of block n, column j)
             np.subtract.at(G, ks.bE_col[a:e], v[:, None] * X[n][ks.bE_row[a:e], 1:])
             np.subtract.at(rb, ks.bE_col[a:e], v * X[n][ks.bE_row[a:e], 0])
-        xb = np.linalg.solve(G, rb)
-        neg += int((np.linalg.eigvalsh(G) < 0).sum())
+        Ginv, ng_ = sym_invert_bp(G)
+        xb = Ginv @ rb
+        neg += ng_
         sol[ub] = xb
     for n in range(N):
         u = ks.unk[ks.blk_ptr[n]:ks.blk_ptr[n + 1]]

@@ -1,0 +1,77 @@
+'''
+GPU: converged raceline solves through the product API (builders -> nlpsol-shaped solver -> batched
+interior-point driver -> CUDA evaluation + KKT kernels), checked against
+  * the golden solutions the same driver produced on the CPU oracle backend (tests/golden/make_golden_ipm.py):
+    lap time within 1e-6 relative (BASELINE.json north_star tolerance for converged results),
+  * the first-order optimality conditions, evaluated independently with the oracle's functions.
+'''
+import os
+
+import numpy as np
+import pytest
+
+from cases import build_case, build_product, make_line
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+LAP_RTOL = 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['race_param_rk4_point', 'race_global_rk4_point'])
+def test_point_mass_solve_matches_cpu_golden(name, built_library):
+    from oracle.nlp_functions import OracleNLP
+    from test_ipm_cpu import _kkt_conditions
+    N = 7
+    prod, ref = build_case(name, N=N)
+    st = prod.structure
+    res = prod.solve()
+    stats = prod.solver.stats()
+    assert stats['success'] and stats['return_status'] == 'Solve_Succeeded'
+    gold = np.load(os.path.join(GOLD, f'ipm_{name}_N{N}.npz'))
+    assert abs(res.time - float(gold['lap'])) <= LAP_RTOL * float(gold['lap'])
+    assert np.abs(prod.sol['x'] - gold['x']).max() <= 1e-5
+    _kkt_conditions(st, OracleNLP(ref, build_hess=False), prod.sol['x'], prod.sol['lam_g'], prod.sol['lam_x'])
+    assert res.feasible and len(res.states) == st.N and abs(sum(res.step_sizes) - res.time) < 1e-12
+
+
+@pytest.mark.gpu
+def test_batched_multistart_solves(built_library):
+    ''' B instances in lock step: identical starts give identical answers, perturbed starts still converge '''
+    prod = build_product('race_param_rk4_point', N=7)
+    st = prod.structure
+    prod.solver.verbose = False
+    rng = np.random.default_rng(0)
+    B = 6
+    X0 = np.tile(st.w0, (B, 1))
+    X0[3:] += 0.02 * rng.standard_normal((B - 3, st.nw))
+    sol = prod.solver(x0=X0, lbx=st.lbw, ubx=st.ubw, lbg=st.lbg, ubg=st.ubg)
+    s = prod.solver.stats()
+    assert s['success_each'].all()
+    assert np.array_equal(sol['x'][0], sol['x'][1]) and np.array_equal(sol['x'][0], sol['x'][2])
+    gold = np.load(os.path.join(GOLD, 'ipm_race_param_rk4_point_N7.npz'))
+    laps = sol['x'][:, :st.N].sum(1)
+    assert abs(laps[0] - float(gold['lap'])) <= LAP_RTOL * float(gold['lap'])
+    g = sol['g']
+    assert (g >= st.lbg - 1e-6).all() and (g <= st.ubg + 1e-6).all()
+
+
+@pytest.mark.gpu
+def test_drone_warm_start_chain(built_library):
+    ''' scripts/race.py pattern at reduced size: point-mass solve -> drone initial guess -> drone solve '''
+    from aircraft_trajectory_optimization_b200 import raceline as RL
+    from aircraft_trajectory_optimization_b200.pytypes import DroneConfig
+    line = make_line('race')
+    cfg = RL.ParametricRacelineConfig(N=7, use_rk4=True, closed=True, verbose=False)
+    cfg.fixed_gates = line.config.s[:-1]
+    solver = RL.ParametricDroneRaceline(line, cfg, DroneConfig(global_r=True, use_quat=True))
+    assert solver.ws_solver.solver.stats()['success']
+    res = solver.solve()
+    st = solver.structure
+    assert solver.solver.stats()['success'] and res.feasible
+    g = solver.sol['g']
+    assert (g >= st.lbg - 1e-6).all() and (g <= st.ubg + 1e-6).all()
+    assert 3.0 < res.time < solver.ws_raceline.time + 1.0
+    # quaternions on the unit sphere at every node after the first (continuity renormalises)
+    q = np.array([s.q.to_vec() for s in res.states[1:]]) if hasattr(res.states[0], 'q') else None
+    if q is not None:
+        assert np.abs(np.linalg.norm(q, axis=1) - 1).max() < 1e-6

@@ -17,7 +17,7 @@ def _inputs(st, F, B, seed=0):
     L = np.stack([eval_point(st, seed + b)[1] for b in range(B)])
     out = F.eval(X, lam_f=np.ones(B), lam_g=L, want=('jac', 'hess'))
     dxd = 1.0 + rng.uniform(0, 1, (B, st.nw))
-    D = np.where(st.lbg == st.ubg, 1e-9, rng.uniform(0.1, 1, (B, st.ng)))
+    D = np.where(st.lbg == st.ubg, 0.0, rng.uniform(0.1, 1, (B, st.ng)))
     rhs = rng.standard_normal((B, st.nw + st.ng))
     return out['hess'], out['jac'], dxd, D, rhs
 
@@ -40,18 +40,26 @@ def test_kkt_solve_matches_sparse_lu(name, built_library):
     assert int(status[:, 0].abs().sum()) == 0
     # K v product against scipy
     kv = K.matvec(th, tj, tdx, tnd, sol).cpu().numpy()
-    # one step of iterative refinement with the stored factors
-    res = tr - K.matvec(th, tj, tdx, tnd, sol)
-    sol2 = sol + K.resolve(th, tj, tdx, tnd, res)
-    sol, sol2 = sol.cpu().numpy(), sol2.cpu().numpy()
+    # iterative refinement with the stored factors
+    sol2 = sol.clone()
+    for _ in range(3):
+        sol2 = sol2 + K.resolve(th, tj, tdx, tnd, tr - K.matvec(th, tj, tdx, tnd, sol2))
+    sol, sol2, status = sol.cpu().numpy(), sol2.cpu().numpy(), status.cpu().numpy()
     for b in range(B):
         Km = kkt_matrix(st, hess[b], jac[b], dxd[b], D[b])
         ref = sparse_solve(st, hess[b], jac[b], dxd[b], D[b], rhs[b])
         scale = np.abs(ref).max()
+        # K v product: bit-for-bit the same sum up to ordering
         assert np.abs(Km @ sol[b] - kv[b]).max() <= 1e-9 * max(1.0, np.abs(kv[b]).max())
-        assert np.abs(sol[b] - ref).max() <= 1e-4 * scale
-        assert np.abs(sol2[b] - ref).max() <= 1e-9 * scale
-        assert np.abs(Km @ sol2[b] - rhs[b]).max() <= 1e-8 * max(1.0, np.abs(rhs[b]).max())
+        # unrefined block solve: limited by the conditioning of the explicit block inverses
+        assert np.abs(sol[b] - ref).max() <= 1e-3 * scale, (np.abs(sol[b] - ref).max(), scale)
+        # refined: residual at fp64 level, solution equal to SuperLU's within conditioning
+        assert np.abs(Km @ sol2[b] - rhs[b]).max() <= 1e-9 * max(1.0, np.abs(rhs[b]).max())
+        assert np.abs(sol2[b] - ref).max() <= 1e-7 * scale, (np.abs(sol2[b] - ref).max(), scale)
+        # inertia: exactly ng negative eigenvalues here (dx_diag > 0 dominates W on these instances?) -- compare
+        # with the count from a dense eigendecomposition
+        neg_ref = int((np.linalg.eigvalsh(Km.toarray()) < 0).sum())
+        assert status[b, 1] == neg_ref, (status[b], neg_ref)
 
 
 @pytest.mark.gpu

@@ -1,0 +1,64 @@
+'''
+The interior-point driver (aircraft_trajectory_optimization_b200/ipm.py) on the CPU oracle backend:
+convergence on a small race.py point-mass instance, the committed golden solution, and an independent
+check of the first-order optimality conditions with the oracle's own functions.
+'''
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from cases import build_case
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def _kkt_conditions(st, nlp, x, lam_g, lam_x, tol=1e-6):
+    ''' CasADi sign convention: grad f + J' lam_g + lam_x = 0, lam >= 0 at upper / <= 0 at lower bounds '''
+    f, gf = nlp.nlp_grad_f(x)
+    g, jv = nlp.nlp_jac_g(x)
+    J = nlp.jac_csc(jv)
+    stat = gf + J.T @ lam_g + lam_x
+    assert np.abs(stat).max() <= tol * max(1.0, np.abs(lam_g).max() / 100)
+    assert (g >= st.lbg - tol).all() and (g <= st.ubg + tol).all()
+    assert (x >= st.lbw - tol).all() and (x <= st.ubw + tol).all()
+    # complementarity: a multiplier is non-zero only at an active bound
+    act_g = np.minimum(g - st.lbg, st.ubg - g)
+    free_g, free_x = np.isinf(act_g), np.isinf(np.minimum(x - st.lbw, st.ubw - x))
+    assert np.abs(lam_g[free_g]).max(initial=0.0) == 0 and np.abs(lam_x[free_x]).max(initial=0.0) == 0
+    ineq = (st.lbg < st.ubg) & ~free_g
+    assert np.abs(lam_g[ineq] * act_g[ineq]).max(initial=0.0) <= 1e-5
+    act_x = np.minimum(x - st.lbw, st.ubw - x)
+    assert np.abs(lam_x[~free_x] * act_x[~free_x]).max(initial=0.0) <= 1e-5
+
+
+def test_point_mass_solve_matches_golden():
+    from oracle.nlp_functions import OracleNLP
+    from oracle.cpu_backend import OracleBackend
+    from aircraft_trajectory_optimization_b200.ipm import InteriorPoint, IpmOptions
+    from aircraft_trajectory_optimization_b200.kkt import build_kkt_structure
+    name, N = 'race_global_rk4_point', 7
+    prod, ref = build_case(name, N=N)
+    st = prod.structure
+    nlp = OracleNLP(ref)
+    be = OracleBackend(nlp, nlp, ks=build_kkt_structure(st))
+    T = lambda a: torch.from_numpy(np.asarray(a, dtype=float))
+    X0 = torch.stack([T(st.w0), T(st.w0)])           # two identical instances advance in lock step
+    r = InteriorPoint(be, IpmOptions(max_iter=200)).solve(X0, T(st.lbw), T(st.ubw), T(st.lbg), T(st.ubg))
+    assert r.success.all() and (r.status == 0).all()
+    assert torch.equal(r.x[0], r.x[1])
+    gold = np.load(os.path.join(GOLD, f'ipm_{name}_N{N}.npz'))
+    lap = float(r.x[0, :st.N].sum())
+    assert abs(lap - float(gold['lap'])) <= 1e-9 * lap
+    assert np.abs(r.x[0].numpy() - gold['x']).max() <= 1e-7
+    _kkt_conditions(st, nlp, r.x[0].numpy(), r.lam_g[0].numpy(), r.lam_x[0].numpy())
+
+
+def test_golden_solutions_are_kkt_points():
+    ''' the committed golden solutions satisfy the optimality conditions of the oracle's NLP '''
+    from oracle.nlp_functions import OracleNLP
+    for name, N in (('race_param_rk4_point', 7), ('race_global_rk4_point', 7)):
+        prod, ref = build_case(name, N=N)
+        gold = np.load(os.path.join(GOLD, f'ipm_{name}_N{N}.npz'))
+        _kkt_conditions(prod.structure, OracleNLP(ref, build_hess=False), gold['x'], gold['lam_g'], gold['lam_x'])
