@@ -64,153 +64,217 @@ __device__ __forceinline__ double kkt_diag(const KktVals& v, int u, int nw) {
 }
 
 // In-place inverse of the SYMMETRIC b x b matrix M (row-major, leading dimension LD, shared memory) by
-// Gauss-Jordan sweeps with Bunch-Parlett pivoting: at every step the largest remaining diagonal entry
-// is compared with the largest remaining off-diagonal entry; a 1x1 pivot is taken when
-// |diag| >= alpha |offdiag| (alpha = (1 + sqrt 17) / 8), otherwise the 2x2 pivot spanned by the largest
-// off-diagonal entry.  Pivots are taken in place (symmetric pivoting only chooses the order), so no
-// permutation has to be undone.  The pivot signs give the inertia: *neg accumulates the number of
-// negative eigenvalues (a 2x2 pivot chosen this way has exactly one); the return value counts
-// vanishing pivots.  The search for the next pivot is fused into the update pass.
-struct KktPivot {
-  double vd, vo;   // largest |diagonal|, largest |off-diagonal| among the unswept part
-  int kd, io, jo;
-};
-
-__device__ __forceinline__ void kkt_pivot_merge(KktPivot& a, double vd, int kd, double vo, int io, int jo) {
-  if (vd > a.vd || (vd == a.vd && kd < a.kd)) {
-    a.vd = vd;
-    a.kd = kd;
-  }
-  if (vo > a.vo || (vo == a.vo && (io < a.io || (io == a.io && jo < a.jo)))) {
-    a.vo = vo;
-    a.io = io;
-    a.jo = jo;
-  }
+// Gauss-Jordan sweeps with Bunch-Kaufman pivoting.
+//
+// Pivot choice (every warp computes it redundantly from shared memory, so no broadcast barrier is needed):
+// k = remaining index with the largest diagonal entry, lambda = largest remaining off-diagonal entry of
+// column k (row r), sigma = the same for column r; 1x1 pivot k when |a_kk| >= alpha lambda or
+// |a_kk| sigma >= alpha lambda^2, 1x1 pivot r when |a_rr| >= alpha sigma, else the 2x2 pivot (k, r);
+// alpha = (1 + sqrt 17) / 8.  The arg-max scans compare float magnitudes with one __reduce_max_sync each.
+// Pivots are taken in place (symmetric pivoting only chooses the order): no permutation to undo.
+//
+// Update: a Gauss-Jordan step on pivot p is the rank-1 update M -= c r' (c_i = a_ip, r_j = a_pj / a_pp) away
+// from the pivot row and column, which are assigned directly (folding them into the rank-1 form cancels
+// catastrophically for large pivots); a 2x2 step on (p, q) is the rank-2 analogue.  Every thread keeps a
+// fixed TR x TC tile of M in registers (columns strided across lanes) and mirrors it to shared memory; the
+// pivot row / column cases are selects on per-tile flags, not branches.
+//
+// The pivot signs give the inertia: *neg accumulates the number of negative eigenvalues (a 2x2 pivot
+// chosen this way has one of each sign); the return value counts vanishing pivots.
+__device__ __forceinline__ void kkt_argmax32(float v, int i, int& arg) {
+  // largest v over the warp (v >= 0 or -1), smallest index on ties; every lane gets the result
+  const unsigned key = __float_as_uint(v < 0.f ? 0.f : v) + (v < 0.f ? 0u : 1u);
+  const unsigned best = __reduce_max_sync(0xffffffffu, key);
+  const unsigned cand = (key == best) ? (unsigned)i : 0x7fffffffu;
+  arg = (int)__reduce_min_sync(0xffffffffu, cand);
 }
 
-// block-wide reduction of the per-thread candidates; the result lands in *out (shared memory)
-__device__ void kkt_pivot_reduce(KktPivot mine, KktPivot* warp_slots, KktPivot* out) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double vd = __shfl_xor_sync(0xffffffffu, mine.vd, o);
-    const int kd = __shfl_xor_sync(0xffffffffu, mine.kd, o);
-    const double vo = __shfl_xor_sync(0xffffffffu, mine.vo, o);
-    const int io = __shfl_xor_sync(0xffffffffu, mine.io, o);
-    const int jo = __shfl_xor_sync(0xffffffffu, mine.jo, o);
-    kkt_pivot_merge(mine, vd, kd, vo, io, jo);
-  }
-  if (lane == 0) warp_slots[warp] = mine;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    KktPivot r = warp_slots[0];
-    for (int w = 1; w < nwarps; ++w) kkt_pivot_merge(r, warp_slots[w].vd, warp_slots[w].kd, warp_slots[w].vo, warp_slots[w].io, warp_slots[w].jo);
-    *out = r;
-  }
-  __syncthreads();
+__device__ __forceinline__ float kkt_mag(double a) {
+  const float f = (float)fabs(a);
+  return f != f ? 0.f : f;          // NaN -> 0
 }
 
-__device__ int kkt_sym_invert(double* M, int LD, int b, double* colp, double* rowp, double* colq, double* rowq,
-                              int* swept, KktPivot* slots, int* neg) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  KktPivot* cur = slots + nwarps;
+template <int TR, int TC>
+__device__ int kkt_sym_invert(double* M, int LD, int b, double* c1, double* r1, double* c2, double* r2,
+                              int* swept, int* neg) {
+  const int tid = threadIdx.x, lane = tid & 31;
   const double alpha = 0.6403882032022076;
   int bad = 0, nneg = 0;
-  for (int i = tid; i < b; i += blockDim.x) swept[i] = 0;
-  // initial search
-  KktPivot mine{-1.0, -1.0, 0x7fffffff, 0x7fffffff, 0x7fffffff};
-  for (int i = warp; i < b; i += nwarps)
-    for (int j = lane; j < b; j += 32) {
-      if (j < i) continue;
-      const double a = fabs(M[i * LD + j]);
-      if (i == j) kkt_pivot_merge(mine, a, i, -1.0, 0x7fffffff, 0x7fffffff);
-      else kkt_pivot_merge(mine, -1.0, 0x7fffffff, a, i, j);
+  const int ntc = (b + TC - 1) / TC, ntr = (b + TR - 1) / TR;
+  const int ti = tid / ntc, tj = tid - ti * ntc;
+  const bool owner = ti < ntr;
+  const int i0 = ti * TR;
+  double m[TR][TC];
+#pragma unroll
+  for (int a = 0; a < TR; ++a)
+#pragma unroll
+    for (int c = 0; c < TC; ++c) {
+      const int i = i0 + a, j = tj + c * ntc;
+      m[a][c] = (owner && i < b && j < b) ? M[i * LD + j] : 0.0;
     }
+  for (int i = tid; i < b; i += blockDim.x) swept[i] = 0;
   __syncthreads();
-  kkt_pivot_reduce(mine, slots, cur);
   int remaining = b;
   while (remaining > 0) {
-    const KktPivot pv = *cur;
-    const bool two = remaining > 1 && !(pv.vd >= alpha * pv.vo);
-    mine = KktPivot{-1.0, -1.0, 0x7fffffff, 0x7fffffff, 0x7fffffff};
-    if (!two) {
-      const int k = pv.kd;
-      double d = M[k * LD + k];
+    // ---------------------------------------------------------------- pivot choice (per warp, redundant)
+    int k, r = 0, type = 1, p, q;
+    {
+      float v = -1.f;
+      int vi = 0x7fffffff;
+      for (int i = lane; i < b; i += 32)
+        if (!swept[i]) {
+          const float a = kkt_mag(M[i * LD + i]);
+          if (a > v) {
+            v = a;
+            vi = i;
+          }
+        }
+      kkt_argmax32(v, vi, k);
+    }
+    p = q = k;
+    if (remaining > 1) {
+      float v = -1.f;
+      int vi = 0x7fffffff;
+      for (int i = lane; i < b; i += 32)
+        if (!swept[i] && i != k) {
+          const float a = kkt_mag(M[i * LD + k]);
+          if (a > v) {
+            v = a;
+            vi = i;
+          }
+        }
+      kkt_argmax32(v, vi, r);
+      const double akk = fabs(M[k * LD + k]), lam = fabs(M[r * LD + k]);
+      if (!(akk >= alpha * lam)) {
+        v = -1.f;
+        vi = 0x7fffffff;
+        for (int i = lane; i < b; i += 32)
+          if (!swept[i] && i != r) {
+            const float a = kkt_mag(M[i * LD + r]);
+            if (a > v) {
+              v = a;
+              vi = i;
+            }
+          }
+        int t;
+        kkt_argmax32(v, vi, t);
+        const double sig = fabs(M[t * LD + r]);
+        if (akk * sig >= alpha * lam * lam) {
+          p = k;
+        } else if (fabs(M[r * LD + r]) >= alpha * sig) {
+          p = r;
+        } else {
+          type = 2;
+          p = k < r ? k : r;
+          q = k < r ? r : k;
+        }
+      }
+    }
+    // ---------------------------------------------------------------- the update vectors
+    if (type == 1) {
+      double d = M[p * LD + p];
       if (!(fabs(d) > 1e-250)) {
         d = 1e-250;
         bad++;
       }
       if (d < 0) nneg++;
       const double di = 1.0 / d;
-      for (int j = tid; j < b; j += blockDim.x) {
-        colp[j] = M[j * LD + k];
-        rowp[j] = M[k * LD + j] * di;
+      if (tid < b) {
+        const int j = tid;
+        c1[j] = M[j * LD + p];
+        r1[j] = (j == p) ? di : M[p * LD + j] * di;
       }
-      if (tid == 0) swept[k] = 1;
       __syncthreads();
-      for (int i = warp; i < b; i += nwarps) {
-        const double ci = colp[i];
-        const bool ui = !swept[i];
-        for (int j = lane; j < b; j += 32) {
-          double v;
-          if (i == k) v = (j == k) ? di : rowp[j];
-          else if (j == k) v = -ci * di;
-          else v = M[i * LD + j] - ci * rowp[j];
-          M[i * LD + j] = v;
-          if (ui && j >= i && !swept[j]) {
-            const double a = fabs(v);
-            if (i == j) kkt_pivot_merge(mine, a, i, -1.0, 0x7fffffff, 0x7fffffff);
-            else kkt_pivot_merge(mine, -1.0, 0x7fffffff, a, i, j);
-          }
+      if (tid == 0) swept[p] = 1;
+      if (owner) {
+        double cc[TR], rr[TC];
+        bool rsel[TR], csel[TC];
+#pragma unroll
+        for (int a = 0; a < TR; ++a) {
+          cc[a] = c1[i0 + a];
+          rsel[a] = (i0 + a == p);
         }
+#pragma unroll
+        for (int c = 0; c < TC; ++c) {
+          rr[c] = r1[tj + c * ntc];
+          csel[c] = (tj + c * ntc == p);
+        }
+#pragma unroll
+        for (int a = 0; a < TR; ++a)
+#pragma unroll
+          for (int c = 0; c < TC; ++c) {
+            // pivot row: a_pj / d (1 / d on the pivot); pivot column: -a_ip / d; elsewhere the rank-1 update
+            double v = csel[c] ? -cc[a] * di : m[a][c] - cc[a] * rr[c];
+            v = rsel[a] ? rr[c] : v;
+            m[a][c] = v;
+            const int i = i0 + a, j = tj + c * ntc;
+            if (i < b && j < b) M[i * LD + j] = v;
+          }
       }
       remaining -= 1;
     } else {
-      const int p = pv.io, q = pv.jo;
       const double epp = M[p * LD + p], epq = M[p * LD + q], eqq = M[q * LD + q];
       double det = epp * eqq - epq * epq;
       if (!(fabs(det) > 1e-250)) {
         det = -1e-250;
         bad++;
       }
-      nneg++;   // |epq| dominates the diagonal: det < 0, one eigenvalue of each sign
-      if (det > 0 && epp + eqq < 0) nneg++;   // (cannot happen with the pivot rule; kept for safety)
-      else if (det > 0) nneg--;
+      nneg += det < 0 ? 1 : (epp + eqq < 0 ? 2 : 0);
       const double i00 = eqq / det, i01 = -epq / det, i11 = epp / det;
-      for (int j = tid; j < b; j += blockDim.x) {
+      if (tid < b) {
+        const int j = tid;
         const double ap = M[p * LD + j], aq = M[q * LD + j];
-        colp[j] = M[j * LD + p];
-        colq[j] = M[j * LD + q];
-        rowp[j] = i00 * ap + i01 * aq;
-        rowq[j] = i01 * ap + i11 * aq;
+        c1[j] = M[j * LD + p];
+        c2[j] = M[j * LD + q];
+        if (j == p) {
+          r1[j] = i00;
+          r2[j] = i01;
+        } else if (j == q) {
+          r1[j] = i01;
+          r2[j] = i11;
+        } else {
+          r1[j] = i00 * ap + i01 * aq;
+          r2[j] = i01 * ap + i11 * aq;
+        }
       }
+      __syncthreads();
       if (tid == 0) {
         swept[p] = 1;
         swept[q] = 1;
       }
-      __syncthreads();
-      for (int i = warp; i < b; i += nwarps) {
-        const double cp = colp[i], cq = colq[i];
-        const bool ui = !swept[i];
-        for (int j = lane; j < b; j += 32) {
-          double v;
-          if (i == p) v = (j == p) ? i00 : ((j == q) ? i01 : rowp[j]);
-          else if (i == q) v = (j == p) ? i01 : ((j == q) ? i11 : rowq[j]);
-          else if (j == p) v = -(cp * i00 + cq * i01);
-          else if (j == q) v = -(cp * i01 + cq * i11);
-          else v = M[i * LD + j] - cp * rowp[j] - cq * rowq[j];
-          M[i * LD + j] = v;
-          if (ui && j >= i && !swept[j]) {
-            const double a = fabs(v);
-            if (i == j) kkt_pivot_merge(mine, a, i, -1.0, 0x7fffffff, 0x7fffffff);
-            else kkt_pivot_merge(mine, -1.0, 0x7fffffff, a, i, j);
-          }
+      if (owner) {
+        double ca[TR], cb[TR], ra[TC], rb[TC];
+        int rsel[TR];
+        bool csel[TC];
+#pragma unroll
+        for (int a = 0; a < TR; ++a) {
+          ca[a] = c1[i0 + a];
+          cb[a] = c2[i0 + a];
+          rsel[a] = (i0 + a == p) ? 1 : ((i0 + a == q) ? 2 : 0);
         }
+#pragma unroll
+        for (int c = 0; c < TC; ++c) {
+          const int j = tj + c * ntc;
+          ra[c] = r1[j];
+          rb[c] = r2[j];
+          csel[c] = (j == p) || (j == q);
+        }
+#pragma unroll
+        for (int a = 0; a < TR; ++a)
+#pragma unroll
+          for (int c = 0; c < TC; ++c) {
+            // pivot rows: E^-1 A_Pj (E^-1 itself on the pivot block); pivot columns: -A_iP E^-1; else rank-2 update
+            const double t = ca[a] * ra[c] + cb[a] * rb[c];
+            double v = csel[c] ? -t : m[a][c] - t;
+            v = rsel[a] == 1 ? ra[c] : (rsel[a] == 2 ? rb[c] : v);
+            m[a][c] = v;
+            const int i = i0 + a, j = tj + c * ntc;
+            if (i < b && j < b) M[i * LD + j] = v;
+          }
       }
       remaining -= 2;
     }
     __syncthreads();
-    if (remaining > 0) kkt_pivot_reduce(mine, slots, cur);
   }
   *neg += nneg;
   return bad;
@@ -218,9 +282,9 @@ __device__ int kkt_sym_invert(double* M, int LD, int b, double* colp, double* ro
 
 struct KktSmem {
   double *M, *Yr, *Zs, *Lc, *YLs, *carry, *rcarry, *colp, *rowp, *colq, *rowq;
-  KktPivot* slots;
   int* swept;
 };
+#define RB_KKT_VPAD 72   // length of the update vectors: largest block (64) + tile overhang
 
 __host__ __device__ inline size_t kkt_smem_doubles(int bmax, int nb, int mmax, int qmax) {
   const int LD = bmax | 1, nrhs = 1 + nb, nbb = nb > bmax ? nb : bmax;
@@ -231,15 +295,14 @@ __host__ __device__ inline size_t kkt_smem_doubles(int bmax, int nb, int mmax, i
   n += (size_t)bmax * mmax;                   // YLs
   n += (size_t)mmax * mmax;                   // carry
   n += (size_t)mmax * nrhs;                   // rcarry
-  n += 4 * (size_t)nbb;                       // colp, rowp, colq, rowq
+  n += 4 * (size_t)RB_KKT_VPAD;               // the update vectors
   (void)LD;
   return n;
 }
 
 __host__ __device__ inline size_t kkt_smem_bytes(int bmax, int nb, int mmax, int qmax) {
   const int nbb = nb > bmax ? nb : bmax;
-  return kkt_smem_doubles(bmax, nb, mmax, qmax) * sizeof(double) + (RB_KKT_THREADS / 32 + 1) * sizeof(KktPivot) +
-         ((size_t)nbb + 4) * sizeof(int);
+  return kkt_smem_doubles(bmax, nb, mmax, qmax) * sizeof(double) + ((size_t)nbb + 4) * sizeof(int);
 }
 
 __device__ inline KktSmem kkt_carve(double* s, int bmax, int nb, int mmax, int qmax) {
@@ -252,16 +315,16 @@ __device__ inline KktSmem kkt_carve(double* s, int bmax, int nb, int mmax, int q
   k.YLs = s; s += (size_t)bmax * mmax;
   k.carry = s; s += (size_t)mmax * mmax;
   k.rcarry = s; s += (size_t)mmax * nrhs;
-  k.colp = s; s += nbb;
-  k.rowp = s; s += nbb;
-  k.colq = s; s += nbb;
-  k.rowq = s; s += nbb;
-  k.slots = reinterpret_cast<KktPivot*>(s);
-  k.swept = reinterpret_cast<int*>(k.slots + RB_KKT_THREADS / 32 + 1);
+  k.colp = s; s += RB_KKT_VPAD;
+  k.rowp = s; s += RB_KKT_VPAD;
+  k.colq = s; s += RB_KKT_VPAD;
+  k.rowq = s; s += RB_KKT_VPAD;
+  k.swept = reinterpret_cast<int*>(s);
   return k;
 }
 
-__global__ void __launch_bounds__(RB_KKT_THREADS)
+template <int TR, int TC>
+__global__ void __launch_bounds__(RB_KKT_THREADS, TR * TC <= 8 ? 3 : 2)
 kkt_factor_solve_kernel(const RbKktDev d, const RbKktBatch bt) {
   extern __shared__ double kkt_smem[];
   const int p = blockIdx.x;
@@ -313,7 +376,7 @@ kkt_factor_solve_kernel(const RbKktDev d, const RbKktBatch bt) {
       }
       __syncthreads();
     }
-    bad += kkt_sym_invert(s.M, LD, b, s.colp, s.rowp, s.colq, s.rowq, s.swept, s.slots, &neg);
+    bad += kkt_sym_invert<TR, TC>(s.M, LD, b, s.colp, s.rowp, s.colq, s.rowq, s.swept, &neg);
 
     // z = S^-1 y  (row i per warp, right-hand sides across lanes)
     for (int i = warp; i < b; i += nwarps) {
@@ -421,7 +484,7 @@ kkt_factor_solve_kernel(const RbKktDev d, const RbKktBatch bt) {
       }
     }
     __syncthreads();
-    bad += kkt_sym_invert(s.M, LD, nb, s.colp, s.rowp, s.colq, s.rowq, s.swept, s.slots, &neg);
+    bad += kkt_sym_invert<TR, TC>(s.M, LD, nb, s.colp, s.rowp, s.colq, s.rowq, s.swept, &neg);
     if (bt.SB)
       for (int i = tid; i < nb * nb; i += blockDim.x) {
         const int r = i / nb, c = i - r * nb;

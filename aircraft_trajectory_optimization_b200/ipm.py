@@ -66,6 +66,8 @@ class IpmOptions:
     delta_c_bar: float = 1e-8
     kappa_c: float = 0.25
     refine_steps: int = 2
+    window: int = 0                    # > 0: at most this many instances iterate at a time; finished ones are
+                                       # replaced from the pending queue (keeps the batched kernels full)
     verbose: bool = False
 
 
@@ -137,9 +139,13 @@ class InteriorPoint:
         res = IpmResult(None, None, None, None, None, None, None, None, None)
         ones_B = torch.ones(B, dtype=dt, device=dev)
 
-        def evaluate(xx, yy, derivs):
+        def evaluate(xx, yy, derivs, mask=None):
+            ''' mask: instances whose values are needed (the others keep their previous values) '''
             t0 = time.perf_counter()
-            out = be.eval(xx, yy, ones_B, derivs)
+            idx = None
+            if mask is not None and not bool(mask.all()):
+                idx = torch.nonzero(mask).squeeze(1)
+            out = be.eval(xx, yy, ones_B, derivs, idx)
             if dev.type == 'cuda':
                 torch.cuda.synchronize(dev)
             res.t_eval += time.perf_counter() - t0
@@ -155,9 +161,12 @@ class InteriorPoint:
         mu = torch.full((B,), o.mu_init, dtype=dt, device=dev)
         zero_h = torch.zeros_like(ev['hess'])
 
-        def kkt(hess, jac, dxd, negd, rhs):
+        def kkt(hess, jac, dxd, negd, rhs, mask=None):
             t0 = time.perf_counter()
-            sol, st = be.kkt_solve(hess, jac, dxd, negd, rhs, o.refine_steps)
+            idx = None
+            if mask is not None and not bool(mask.all()):
+                idx = torch.nonzero(mask).squeeze(1)
+            sol, st = be.kkt_solve(hess, jac, dxd, negd, rhs, o.refine_steps, idx)
             if dev.type == 'cuda':
                 torch.cuda.synchronize(dev)
             res.t_kkt += time.perf_counter() - t0
@@ -219,7 +228,9 @@ class InteriorPoint:
         filt_phi[:, 0] = -float('inf')
         filt_n[:] = 1
         delta_w_last = torch.zeros(B, dtype=dt, device=dev)
-        status = torch.full((B,), -1, dtype=torch.long, device=dev)
+        status = torch.full((B,), -1, dtype=torch.long, device=dev)      # -1 iterating, -2 pending, >= 0 finished
+        if 0 < o.window < B:
+            status[o.window:] = -2
         iters = torch.zeros(B, dtype=torch.long, device=dev)
         acc_count = torch.zeros(B, dtype=torch.long, device=dev)
         ls_fail = torch.zeros(B, dtype=torch.long, device=dev)
@@ -234,7 +245,7 @@ class InteriorPoint:
 
         it = 0
         while True:
-            active = status < 0
+            active = status == -1
             # ---- convergence and barrier update --------------------------------------------------------
             E0, dual0, prim0, comp0 = errors(ev, x, s, y, zL, zU, vL, vU, torch.zeros_like(mu))
             done = active & (E0 <= o.tol)
@@ -243,14 +254,22 @@ class InteriorPoint:
             acc_count = torch.where(acc, acc_count + 1, torch.zeros_like(acc_count))
             done_acc = acc & (acc_count >= o.acceptable_iter)
             status[done_acc] = 1
-            active = status < 0
+            active = status == -1
             if o.verbose:
                 k = 0
                 print(f'{it:4d} f={float(ev["f"][k]):.8e} inf_pr={float(prim0[k]):.2e} inf_du={float(dual0[k]):.2e} '
                       f'compl={float(comp0[k]):.2e} lg(mu)={np.log10(float(mu[k])):.1f} dw={float(delta_w_last[k]):.1e} '
                       f'active={int(active.sum())}')
-            res.history.append((it, int(active.sum())))
-            if not bool(active.any()) or it >= o.max_iter:
+            # refill the window from the pending queue
+            n_act = int(active.sum())
+            if o.window > 0 and n_act < o.window:
+                pend = torch.nonzero(status == -2).squeeze(1)
+                if pend.numel():
+                    status[pend[:o.window - n_act]] = -1
+                    active = status == -1
+                    n_act = int(active.sum())
+            res.history.append((it, n_act))
+            if n_act == 0:
                 break
             for _ in range(4):
                 Emu = errors(ev, x, s, y, zL, zU, vL, vU, mu)[0]
@@ -288,13 +307,9 @@ class InteriorPoint:
                 Ss_reg = torch.where(ineq, Ss + dw_c, torch.ones_like(Ss))
                 negd = torch.where(ineq, -1.0 / Ss_reg, torch.zeros_like(Ss)) - delta_c[:, None]
                 rhs = torch.cat([-r_x, torch.where(ineq, -c - r_s / Ss_reg, -c)], dim=1)
-                sol, st = kkt(ev['hess'], ev['jac'], Sx + dw_c, negd, rhs)
+                sol, st = kkt(ev['hess'], ev['jac'], Sx + dw_c, negd, rhs, need)
                 if o.verbose and attempt >= 1:
                     print(f'        attempt {attempt}: dw={float(delta_w[0]):.2e} dc={float(delta_c[0]):.2e} bad_piv={int(st[0, 0])} neg={int(st[0, 1])} (want {m})')
-                if attempt == 0 and it == int(__import__("os").environ.get("RB_IPM_DUMP_IT", "-1")):
-                    import os
-                    if os.environ.get('RB_IPM_DUMP'):
-                        torch.save(dict(hess=ev['hess'], jac=ev['jac'], Sx=Sx, Ss=Ss, ineq=ineq, x=x, y=y), os.environ['RB_IPM_DUMP'])
                 dx_t, dy_t = sol[:, :n], sol[:, n:]
                 ds_t = torch.where(ineq, (dy_t - r_s) / Ss_reg, torch.zeros_like(s))
                 finite = torch.isfinite(sol).all(1)
@@ -325,7 +340,7 @@ class InteriorPoint:
                 need = need & ~hopeless
                 if not bool(need.any()):
                     break
-            active = status < 0
+            active = status == -1
             am = active[:, None]
             dx, ds, dy = dx * am, ds * am, dy * am
 
@@ -357,7 +372,7 @@ class InteriorPoint:
             for ls in range(o.max_ls):
                 xt = x + alpha[:, None] * dx
                 st_ = torch.where(ineq, s + alpha[:, None] * ds, ceq)
-                evt = evaluate(xt, y, False)
+                evt = evaluate(xt, y, False, searching)
                 th_t = infeas(evt['g'], st_).abs().sum(1)
                 ph_t = barrier(evt['f'], xt, st_, mu)
                 okfin = torch.isfinite(th_t) & torch.isfinite(ph_t)
@@ -408,11 +423,14 @@ class InteriorPoint:
             zL, zU, vL, vU = reset(zL, dL, fL), reset(zU, dU, fU), reset(vL, eL, sfL), reset(vU, eU, sfU)
             iters = iters + active.long()
             it += 1
+            status[(status == -1) & (iters >= o.max_iter)] = 2
+            active = status == -1
             if o.verbose:
                 print(f'      alpha_pr={float(accepted_alpha[0]):.3e} a_max={float(a_pr[0]):.3e} alpha_du={float(a_du[0]):.3e} '
                       f'ls={ls + 1} failed={bool(failed[0])} theta={float(theta[0]):.3e} dphi={float(dphi[0]):.3e} '
                       f'|dx|={float(dx[0].abs().max()):.2e} |dy|={float(dy[0].abs().max()):.2e} attempts={attempt + 1}')
-            ev = evaluate(x, y, True)
+            if bool(active.any()):
+                ev = evaluate(x, y, True, active)
 
         status[status < 0] = 2
         E0 = errors(ev, x, s, y, zL, zU, vL, vU, torch.zeros_like(mu))[0]
@@ -443,31 +461,58 @@ class CudaBackend:
             self._buf[name] = t
         return t
 
-    def eval(self, x, lam_g, lam_f, derivs):
+    def _vp_rows(self, idx):
+        return self.vp if (idx is None or self.vp.dim() == 1) else self.vp[idx].contiguous()
+
+    def eval(self, x, lam_g, lam_f, derivs, idx=None):
+        """ idx: evaluate only these instances; the other rows of the returned tensors keep older values """
         st, dev, B = self.st, x.device, x.shape[0]
-        x = x.contiguous()
-        f, g = self._out('f', (B,), dev), self._out('g', (B, st.ng), dev)
+        f64 = dict(dtype=torch.float64, device=dev)
+        names = ('f', 'grad_f', 'g', 'jac', 'hess') if derivs else ('f', 'g')
+        shapes = dict(f=(B,), grad_f=(B, st.nw), g=(B, st.ng), jac=(B, st.nnz_jac), hess=(B, st.nnz_hess))
+        tag = 'd_' if derivs else 't_'
+        full = {}
+        for k in names:
+            t = self._buf.get(tag + k)
+            if t is None or tuple(t.shape) != shapes[k] or t.device != dev:
+                t = torch.zeros(shapes[k], **f64)
+                self._buf[tag + k] = t
+            full[k] = t
+        if idx is None:
+            xc, lc, out = x.contiguous(), (lam_g.contiguous() if derivs else None), full
+        else:
+            Bc = idx.numel()
+            xc, lc = x[idx].contiguous(), (lam_g[idx].contiguous() if derivs else None)
+            out = {k: torch.empty((Bc,) + shapes[k][1:], **f64) for k in names}
+        lf = None if not derivs else (lam_f if idx is None else lam_f[idx].contiguous())
+        self._scratch = self.F.eval_device(xc, lc, lf, self._vp_rows(idx), None, out['f'], out.get('grad_f'), out['g'],
+                                           out.get('jac'), out.get('hess'), None)
+        if idx is not None:
+            for k in names:
+                full[k].index_copy_(0, idx, out[k])
         if derivs:
-            gf = torch.empty(B, st.nw, dtype=torch.float64, device=dev)
-            jac = torch.empty(B, st.nnz_jac, dtype=torch.float64, device=dev)
-            hess = torch.empty(B, st.nnz_hess, dtype=torch.float64, device=dev)
-            f, g = torch.empty(B, dtype=torch.float64, device=dev), torch.empty(B, st.ng, dtype=torch.float64, device=dev)
-            self._scratch = self.F.eval_device(x, lam_g.contiguous(), lam_f, self.vp, None, f, gf, g, jac, hess,
-                                               getattr(self, '_scratch', None))
-            return dict(f=f, grad_f=gf, g=g, jac=jac, hess=hess)
-        f, g = torch.empty(B, dtype=torch.float64, device=dev), torch.empty(B, st.ng, dtype=torch.float64, device=dev)
-        self._scratch = self.F.eval_device(x, None, None, self.vp, None, f, None, g, None, None,
-                                           getattr(self, '_scratch', None))
-        return dict(f=f, g=g)
+            # the driver keeps these until the next derivative evaluation: hand out the persistent buffers
+            return dict(full)
+        return {k: v.clone() for k, v in full.items()}
 
     def kkt_matvec(self, hess, jac, dx_diag, neg_d, vec):
         return self.K.matvec(hess, jac, dx_diag.contiguous(), neg_d.contiguous(), vec.contiguous())
 
-    def kkt_solve(self, hess, jac, dx_diag, neg_d, rhs, refine_steps):
+    def kkt_solve(self, hess, jac, dx_diag, neg_d, rhs, refine_steps, idx=None):
+        B = rhs.shape[0]
+        if idx is not None:
+            hess, jac, dx_diag, neg_d, rhs = hess[idx], jac[idx], dx_diag[idx], neg_d[idx], rhs[idx]
         dx_diag, neg_d, rhs = dx_diag.contiguous(), neg_d.contiguous(), rhs.contiguous()
         sol, status = self.K.factor_solve(hess, jac, dx_diag, neg_d, rhs)
         sol = sol.clone()
         for _ in range(refine_steps):
             r = rhs - self.K.matvec(hess, jac, dx_diag, neg_d, sol)
             sol = sol + self.K.resolve(hess, jac, dx_diag, neg_d, r)
-        return sol, status
+        if idx is None:
+            return sol, status
+        sol_f = torch.zeros(B, sol.shape[1], dtype=sol.dtype, device=sol.device)
+        st_f = torch.zeros(B, 2, dtype=status.dtype, device=sol.device)
+        st_f[:, 1] = self.ng
+        sol_f.index_copy_(0, idx, sol)
+        st_f.index_copy_(0, idx, status)
+        return sol_f, st_f

@@ -156,6 +156,126 @@ def cpu_port_rate(seconds_budget=12.0, nthreads=0, sample_intervals=49):
     return rate, cores, sample
 
 
+
+def build_c2_with_warm_start():
+    ''' scripts/race.py second solve: parametric quaternion drone, RK4, warm-started from the point-mass solve '''
+    from cases import make_line
+    from aircraft_trajectory_optimization_b200 import raceline as RL
+    from aircraft_trajectory_optimization_b200.pytypes import DroneConfig
+    line = make_line('race')
+    cfg = RL.ParametricRacelineConfig(N=70, use_rk4=True, closed=True, verbose=False)
+    cfg.fixed_gates = line.config.s[:-1]
+    return RL.ParametricDroneRaceline(line, cfg, DroneConfig(global_r=True, use_quat=True))
+
+
+def multistart_inputs(st, vp0, B, seed0, nz=13, nu=4):
+    ''' w0_b = clip(w0_ws + 0.05 * scale * N(0,1)), vehicle parameters x U[0.9, 1.1] '''
+    S = nz + 2 * nu
+    scale = np.zeros(st.nw)
+    scale[:st.N] = st.w0[:st.N]                                   # h: h0
+    per = np.array([0, .5, .5, .1, .1, .1, .1, 1, 1, 1, .5, .5, .5, 1, 1, 1, 1, 0, 0, 0, 0])   # s pinned, du: 0
+    scale[st.N:] = np.tile(per, (st.nw - st.N) // S)
+    X0 = np.empty((B, st.nw))
+    VP = np.empty((B, len(vp0)))
+    for b in range(B):
+        rng = np.random.default_rng(seed0 + b)
+        X0[b] = np.clip(st.w0 + (0.05 * scale * rng.standard_normal(st.nw) if seed0 + b > 0 else 0.0), st.lbw, st.ubw)
+        sc = np.ones(len(vp0))
+        if seed0 + b > 0:
+            sc[[0, 2, 3, 4, 5, 6]] = np.random.default_rng(10_000 + seed0 + b).uniform(0.9, 1.1, 6)
+        VP[b] = vp0 * sc
+    return X0, VP
+
+
+def cpu_iteration_seconds(prod, n_rep=2):
+    '''
+    one interior-point iteration of the C2 drone NLP on ONE host core, the way the reference's CPU path
+    spends it: interpreted evaluation of grad_f, jac_g, hess_l (flat tapes, CasADi's SX-VM execution model)
+    on a 49-interval sample scaled to 490, plus a sparse direct factorisation + solve of the full-size KKT
+    matrix (scipy SuperLU standing in for MUMPS / MA97).
+    '''
+    from cases import build_oracle
+    from oracle.nlp_functions import OracleNLP
+    from oracle.kkt_blocks_ref import kkt_matrix
+    import scipy.sparse.linalg as spla
+    ref = build_oracle(CASE, N=7)
+    nlp = OracleNLP(ref)
+    IN = np.zeros((1, nlp.n_in))
+    IN[0, :nlp.nw] = ref.w0
+    IN[0, -1] = 1.0
+    t0 = time.perf_counter()
+    for _ in range(n_rep):
+        nlp.t_grad_f.batch(IN, 1), nlp.t_jac_g.batch(IN, 1), nlp.t_hess_l.batch(IN, 1)
+    t_eval = (time.perf_counter() - t0) / n_rep * (490 / ref.config.N)
+    st = prod.structure
+    x = st.w0
+    out = prod.functions.eval(x, lam_f=1.0, lam_g=np.ones(st.ng), want=('jac', 'hess'))
+    K = kkt_matrix(st, out['hess'], out['jac'], np.ones(st.nw), np.where(st.lbg == st.ubg, 0.0, 1.0)).tocsc()
+    t0 = time.perf_counter()
+    for _ in range(n_rep):
+        spla.splu(K).solve(np.ones(st.nw + st.ng))
+    t_kkt = (time.perf_counter() - t0) / n_rep
+    return t_eval, t_kkt
+
+
+def run_solves(args, dev, rank, world, dist):
+    ''' converged raceline solves/s on a multi-start x vehicle-parameter batch of C2 (the C5 shape) '''
+    import torch
+    from aircraft_trajectory_optimization_b200.models import vehicle_params
+    t_build = time.perf_counter()
+    prod = build_c2_with_warm_start()                 # includes the point-mass warm-start solve on the GPU
+    t_build = time.perf_counter() - t_build
+    st = prod.structure
+    vp0 = vehicle_params(prod.vehicle_config)
+    B = args.solves_batch
+    X0, VP = multistart_inputs(st, vp0, B, seed0=rank * B)
+    prod.solver.verbose = False
+    prod.solver.max_iter = args.solves_max_iter
+    from aircraft_trajectory_optimization_b200.ipm import IpmOptions
+    prod.solver.options = IpmOptions(window=args.solves_window)
+    lib_launch0 = prod.functions.launch_count()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    sol = prod.solver(x0=X0, lbx=st.lbw, ubx=st.ubw, lbg=st.lbg, ubg=st.ubg, p=VP)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    s = prod.solver.stats()
+    ok = s['success_each']
+    t = torch.tensor([e0.elapsed_time(e1) * 1e-3, float(ok.sum())], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        t[0] = tmax[0]
+    laps = sol['x'][:, :st.N].sum(1)
+    out = dict(value=float(t[1]) / float(t[0]), unit='converged solves/s', instances=world * B, window=args.solves_window,
+               converged=int(t[1]), seconds=float(t[0]), ip_iterations=int(s['iter_count']),
+               iterations_median=float(np.median(s['iterations_each'][ok])) if ok.any() else None,
+               kkt_factorisations=int(s['n_factor']), evaluations=int(s['n_eval']),
+               t_eval_s=s['t_wall_nlp_hess_l'], t_kkt_s=s['t_wall_linear_solver'],
+               lap_time_nominal=float(laps[0]), lap_time_min=float(laps[ok].min()) if ok.any() else None,
+               lap_time_max=float(laps[ok].max()) if ok.any() else None,
+               warm_start_setup_s=t_build, gpu_launches=int(prod.functions.launch_count() - lib_launch0),
+               workload='C5 shape: C2 x multi-start (w0_ws + 0.05*scale*N(0,1)) x vehicle parameters U[0.9,1.1]; '
+                        'instance 0 of rank 0 is the nominal race.py problem')
+    if rank == 0 and not args.no_cpu:
+        t_eval, t_kkt = cpu_iteration_seconds(prod)
+        cores = len(os.sched_getaffinity(0))
+        its = out['iterations_median'] or out['ip_iterations']
+        fac_per_it = s['n_factor'] / max(1, s['iter_count'])
+        ev_per_it = s['n_eval'] / max(1, s['iter_count'])
+        per_solve = its * (t_eval * min(ev_per_it, 1.5) + t_kkt * fac_per_it)
+        out['cpu_baseline'] = dict(value=cores / per_solve, unit='converged solves/s', cores=cores, kind='port',
+                                   sample=f'one IP iteration on one core: tape evaluation {t_eval * 1e3:.1f} ms (49-interval '
+                                          f'sample x10) + SuperLU factor/solve of the {st.nw + st.ng}-dim KKT matrix '
+                                          f'{t_kkt * 1e3:.1f} ms x {fac_per_it:.2f} factorisations/iteration; x {its:.0f} '
+                                          f'iterations (median of the GPU run); one solve per core on {cores} cores')
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -187,6 +307,10 @@ def main():
     ap.add_argument('--batch', type=int, default=2048, help='problem instances per GPU per step')
     ap.add_argument('--e2e-batch', type=int, default=256)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-solves', action='store_true', help='skip the converged-solves leg')
+    ap.add_argument('--solves-batch', type=int, default=1024, help='multi-start instances per GPU in the solves leg')
+    ap.add_argument('--solves-window', type=int, default=888, help='instances iterating at a time (continuous batching)')
+    ap.add_argument('--solves-max-iter', type=int, default=600)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
@@ -299,6 +423,14 @@ def main():
     # spot check: the host path and the device path agree bit for bit on instance 0
     assert np.array_equal(hh[0].numpy(), h_d[0].cpu().numpy()) and np.array_equal(hj[0].numpy(), j_d[0].cpu().numpy())
 
+    solves = None
+    if not args.no_solves:
+        del x_d, l_d, j_d, h_d, gf_d, g_d
+        torch.cuda.empty_cache()
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):      # the builders print progress like the reference does
+            solves = run_solves(args, dev, rank, world, dist)
+
     if rank == 0:
         peak, peak_src = _peaks()
         ab = algorithmic_bytes(st)
@@ -331,7 +463,7 @@ def main():
                                 parallelism=f'{world} x independent instance shards, no collective on the data path'),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              instances_per_step=Be, api='rb_nlp_eval_all (host buffers, pinned)'),
-                    gpu_launches=launches, clocks=clocks, roofline=roofline, cpu_baseline=cpu)
+                    gpu_launches=launches, clocks=clocks, roofline=roofline, cpu_baseline=cpu, solves=solves)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -24,7 +24,7 @@ class OracleBackend:
         self.ng = nlp.ng
         self.nw = nlp.nw
 
-    def eval(self, x, lam_g, lam_f, derivs):
+    def eval(self, x, lam_g, lam_f, derivs, idx=None):
         B = x.shape[0]
         nlp = self.nlp
         IN = np.zeros((B, nlp.n_in))
@@ -50,12 +50,12 @@ class OracleBackend:
             out[b] = K @ vec[b].numpy()
         return torch.from_numpy(out)
 
-    def kkt_solve(self, hess, jac, dx_diag, neg_d, rhs, refine_steps):
+    def kkt_solve(self, hess, jac, dx_diag, neg_d, rhs, refine_steps, idx=None):
         B = rhs.shape[0]
-        sol = np.empty(rhs.shape)
+        sol = np.zeros(rhs.shape)
         status = np.zeros((B, 2), dtype=np.int32)
         status[:, 1] = self.ng
-        for b in range(B):
+        for b in (range(B) if idx is None else idx.tolist()):
             K = kkt_matrix(self.st, hess[b].numpy(), jac[b].numpy(), dx_diag[b].numpy(), -neg_d[b].numpy())
             r = rhs[b].numpy()
             if self.ks is not None:

@@ -40,23 +40,37 @@ def _gather(ks, src, hess, jac, dx_diag, neg_d):
 def sym_invert_bp(A):
     '''
     inverse and number of negative eigenvalues of the symmetric matrix A by Gauss-Jordan sweeps with
-    Bunch-Parlett pivoting -- the numpy twin of kkt_sym_invert in csrc/kkt_blocks.cuh
+    Bunch-Kaufman pivoting -- the numpy twin of kkt_sym_invert in csrc/kkt_blocks.cuh
     '''
     M = np.array(A, dtype=float)
     b = M.shape[0]
     alpha = 0.6403882032022076
     unswept = np.ones(b, dtype=bool)
     neg = 0
+
+    def argmax_col(c, skip):
+        v = np.where(unswept, np.abs(M[:, c]), -1.0)
+        v[skip] = -1.0
+        i = int(np.argmax(v))
+        return v[i], i
+
     while unswept.any():
-        idx = np.nonzero(unswept)[0]
-        sub = np.abs(M[np.ix_(idx, idx)])
-        dg = np.diag(sub)
-        kd = idx[int(np.argmax(dg))]
-        vd = dg.max()
-        off = sub - np.diag(dg)
-        vo = off.max() if len(idx) > 1 else -1.0
-        if len(idx) == 1 or vd >= alpha * vo:
-            k = kd
+        dg = np.where(unswept, np.abs(np.diag(M)), -1.0)
+        k = int(np.argmax(dg))
+        vk = dg[k]
+        piv = (k,)
+        if unswept.sum() > 1:
+            lam, r = argmax_col(k, k)
+            if not vk >= alpha * lam:
+                sig, _ = argmax_col(r, r)
+                if vk * sig >= alpha * lam * lam:
+                    piv = (k,)
+                elif abs(M[r, r]) >= alpha * sig:
+                    piv = (r,)
+                else:
+                    piv = (min(k, r), max(k, r))
+        if len(piv) == 1:
+            k = piv[0]
             d = M[k, k]
             if not abs(d) > 1e-250:
                 d = 1e-250
@@ -69,8 +83,7 @@ def sym_invert_bp(A):
             M[k, k] = 1.0 / d
             unswept[k] = False
         else:
-            io, jo = np.unravel_index(int(np.argmax(np.triu(off, 1))), off.shape)
-            p, q = idx[io], idx[jo]
+            p, q = piv
             E = M[np.ix_([p, q], [p, q])]
             det = E[0, 0] * E[1, 1] - E[0, 1] ** 2
             if not abs(det) > 1e-250:
