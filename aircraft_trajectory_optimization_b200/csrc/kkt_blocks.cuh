@@ -112,52 +112,33 @@ __device__ int kkt_sym_invert(double* M, int LD, int b, double* c1, double* r1, 
       const int i = i0 + a, j = tj + c * ntc;
       m[a][c] = (owner && i < b && j < b) ? M[i * LD + j] : 0.0;
     }
-  for (int i = tid; i < b; i += blockDim.x) swept[i] = 0;
+  unsigned swept_lo = 0u, swept_hi = 0u;   // bit i: index i / i + 32 has been pivoted
+  (void)swept;
   __syncthreads();
   int remaining = b;
   while (remaining > 0) {
     // ---------------------------------------------------------------- pivot choice (per warp, redundant)
+    // lane l looks at indices l and l + 32 (blocks have at most 64 unknowns); `alive` bits live in registers
     int k, r = 0, type = 1, p, q;
+    const int ia = lane, ib = lane + 32;
+    const bool la = ia < b && !((swept_lo >> lane) & 1u), lb = ib < b && !((swept_hi >> lane) & 1u);
     {
-      float v = -1.f;
-      int vi = 0x7fffffff;
-      for (int i = lane; i < b; i += 32)
-        if (!swept[i]) {
-          const float a = kkt_mag(M[i * LD + i]);
-          if (a > v) {
-            v = a;
-            vi = i;
-          }
-        }
-      kkt_argmax32(v, vi, k);
+      const float va = la ? kkt_mag(M[ia * LD + ia]) : -1.f, vb = lb ? kkt_mag(M[ib * LD + ib]) : -1.f;
+      kkt_argmax32(vb > va ? vb : va, vb > va ? ib : ia, k);
     }
     p = q = k;
     if (remaining > 1) {
-      float v = -1.f;
-      int vi = 0x7fffffff;
-      for (int i = lane; i < b; i += 32)
-        if (!swept[i] && i != k) {
-          const float a = kkt_mag(M[i * LD + k]);
-          if (a > v) {
-            v = a;
-            vi = i;
-          }
-        }
-      kkt_argmax32(v, vi, r);
+      {
+        const float va = (la && ia != k) ? kkt_mag(M[ia * LD + k]) : -1.f;
+        const float vb = (lb && ib != k) ? kkt_mag(M[ib * LD + k]) : -1.f;
+        kkt_argmax32(vb > va ? vb : va, vb > va ? ib : ia, r);
+      }
       const double akk = fabs(M[k * LD + k]), lam = fabs(M[r * LD + k]);
       if (!(akk >= alpha * lam)) {
-        v = -1.f;
-        vi = 0x7fffffff;
-        for (int i = lane; i < b; i += 32)
-          if (!swept[i] && i != r) {
-            const float a = kkt_mag(M[i * LD + r]);
-            if (a > v) {
-              v = a;
-              vi = i;
-            }
-          }
+        const float va = (la && ia != r) ? kkt_mag(M[ia * LD + r]) : -1.f;
+        const float vb = (lb && ib != r) ? kkt_mag(M[ib * LD + r]) : -1.f;
         int t;
-        kkt_argmax32(v, vi, t);
+        kkt_argmax32(vb > va ? vb : va, vb > va ? ib : ia, t);
         const double sig = fabs(M[t * LD + r]);
         if (akk * sig >= alpha * lam * lam) {
           p = k;
@@ -169,6 +150,11 @@ __device__ int kkt_sym_invert(double* M, int LD, int b, double* c1, double* r1, 
           q = k < r ? r : k;
         }
       }
+    }
+    // every thread marks the pivots in its own copy of the bitmask
+    if (p < 32) swept_lo |= 1u << p; else swept_hi |= 1u << (p - 32);
+    if (type == 2) {
+      if (q < 32) swept_lo |= 1u << q; else swept_hi |= 1u << (q - 32);
     }
     // ---------------------------------------------------------------- the update vectors
     if (type == 1) {
@@ -185,7 +171,6 @@ __device__ int kkt_sym_invert(double* M, int LD, int b, double* c1, double* r1, 
         r1[j] = (j == p) ? di : M[p * LD + j] * di;
       }
       __syncthreads();
-      if (tid == 0) swept[p] = 1;
       if (owner) {
         double cc[TR], rr[TC];
         bool rsel[TR], csel[TC];
@@ -238,10 +223,6 @@ __device__ int kkt_sym_invert(double* M, int LD, int b, double* c1, double* r1, 
         }
       }
       __syncthreads();
-      if (tid == 0) {
-        swept[p] = 1;
-        swept[q] = 1;
-      }
       if (owner) {
         double ca[TR], cb[TR], ra[TC], rb[TC];
         int rsel[TR];
@@ -378,13 +359,37 @@ kkt_factor_solve_kernel(const RbKktDev d, const RbKktBatch bt) {
     }
     bad += kkt_sym_invert<TR, TC>(s.M, LD, b, s.colp, s.rowp, s.colq, s.rowq, s.swept, &neg);
 
-    // z = S^-1 y  (row i per warp, right-hand sides across lanes)
-    for (int i = warp; i < b; i += nwarps) {
-      for (int r = lane; r < nrhs; r += 32) {
-        double acc = 0.0;
-        for (int j = 0; j < b; ++j) acc += s.M[i * LD + j] * s.Yr[j * nrhs + r];
-        s.Zs[i * nrhs + r] = acc;
-        X_g[((size_t)n * bmax + i) * nrhs + r] = acc;
+    // z = S^-1 y: 2 x 4 output tiles per thread (rows i0, i0+1; right-hand sides strided across lanes)
+    {
+      const int nct = (nrhs + 3) >> 2, nrt = (b + 1) >> 1;
+      for (int tile = tid; tile < nrt * nct; tile += blockDim.x) {
+        const int tr_ = tile / nct, tc_ = tile - tr_ * nct;
+        const int i0 = tr_ * 2, i1 = (i0 + 1 < b) ? i0 + 1 : i0;
+        int rc[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) rc[c] = (tc_ + c * nct < nrhs) ? tc_ + c * nct : tc_;
+        double acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+        for (int j = 0; j < b; ++j) {
+          const double m0 = s.M[i0 * LD + j], m1 = s.M[i1 * LD + j];
+          const double* __restrict__ yj = s.Yr + j * nrhs;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const double y = yj[rc[c]];
+            acc[0][c] += m0 * y;
+            acc[1][c] += m1 * y;
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (tc_ + c * nct < nrhs) {
+            s.Zs[i0 * nrhs + rc[c]] = acc[0][c];
+            X_g[((size_t)n * bmax + i0) * nrhs + rc[c]] = acc[0][c];
+            if (i0 + 1 < b) {
+              s.Zs[i1 * nrhs + rc[c]] = acc[1][c];
+              X_g[((size_t)n * bmax + i1) * nrhs + rc[c]] = acc[1][c];
+            }
+          }
+        }
       }
     }
     // keep the inverse
