@@ -204,6 +204,57 @@ def generate_variant(variant: Variant, out_dir=GEN_DIR):
         [f'f[{i}]' for i in range(nz)] + [f'Jst[tj[{i}]]' for i in range(len(pf.J))]
         + [f'Hst[th[{i}]]' for i in range(len(pf.W))])
     parts.append(code)
+    # ---- materialised form for the two-kernel shooting path (csrc/rk4_cells.cuh) ------------------
+    # fJ_s / vjpW_s write the non-zeros of J and W straight into a strided scratch column (stride RB_SCR_STRIDE);
+    # jmul / jtmul / wmul are the sparse products the direction threads run against those columns.
+    code, ops['fJ_s'] = _emit_fn(pf, 'fJ_s', [cx, cfc, cvp, 'double* __restrict__ f', 'double* __restrict__ Js'],
+                                 pf.f + pf.J_nodes,
+                                 [f'f[{i}]' for i in range(nz)] + [f'Js[{i} * RB_SCR_STRIDE]' for i in range(len(pf.J))])
+    parts.append(code)
+    code, ops['vjpW_s'] = _emit_fn(pf, 'vjpW_s', [cx, 'const double* __restrict__ kb', cfc, cvp,
+                                                  'double* __restrict__ xb', 'double* __restrict__ Ws'],
+                                   pf.xb + pf.W_nodes,
+                                   [f'xb[{i}]' for i in range(nx)] + [f'Ws[{i} * RB_SCR_STRIDE]' for i in range(len(pf.W))])
+    parts.append(code)
+
+    def sparse_product(fname, sig, lines_fn, nops):
+        body = '\n'.join('    ' + ln for ln in lines_fn())
+        return (f'  // {nops} multiply-adds\n  __device__ __forceinline__ static void {fname}({sig}) {{\n{body}\n  }}\n')
+
+    def jmul_lines():
+        out = []
+        for r in range(nz):
+            terms = [f'Js[{e} * RB_SCR_STRIDE] * dx[{c}]' for e, (rr, c) in enumerate(pf.J) if rr == r]
+            out.append(f'dk[{r}] = ' + (' + '.join(terms) if terms else '0.0') + ';')
+        return out
+
+    def jtmul_lines():
+        out = []
+        for c in range(nx):
+            terms = [f'Js[{e} * RB_SCR_STRIDE] * dkb[{r}]' for e, (r, cc) in enumerate(pf.J) if cc == c]
+            if terms:
+                out.append(f'dxb[{c}] += ' + ' + '.join(terms) + ';')
+        return out
+
+    def wmul_lines():
+        out = []
+        for i in range(nx):
+            terms = []
+            for e, (r, c) in enumerate(pf.W):
+                if r == i:
+                    terms.append(f'Ws[{e} * RB_SCR_STRIDE] * dx[{c}]')
+                elif c == i:
+                    terms.append(f'Ws[{e} * RB_SCR_STRIDE] * dx[{r}]')
+            out.append(f'dxb[{i}] = ' + (' + '.join(terms) if terms else '0.0') + ';')
+        return out
+
+    cJs, cWs = 'const double* __restrict__ Js', 'const double* __restrict__ Ws'
+    parts.append(sparse_product('jmul', f'{cJs}, const double* __restrict__ dx, double* __restrict__ dk',
+                                jmul_lines, len(pf.J)))
+    parts.append(sparse_product('wmul', f'{cWs}, const double* __restrict__ dx, double* __restrict__ dxb',
+                                wmul_lines, 2 * len(pf.W)))
+    parts.append(sparse_product('jtmul', f'{cJs}, const double* __restrict__ dkb, double* __restrict__ dxb',
+                                jtmul_lines, len(pf.J)))
 
     def table(tname, vals):
         return f'  static constexpr signed char {tname}[{max(len(vals), 1)}] = {{' \
@@ -212,7 +263,7 @@ def generate_variant(variant: Variant, out_dir=GEN_DIR):
     hdr = (f'// GENERATED by aircraft_trajectory_optimization_b200/codegen.py -- do not edit.\n'
            f'// variant {name}: reference equations drone3d/dynamics/drone_models.py:47-123,249-292,\n'
            f'// point_model.py:28-75,149-213, rotations.py:44-102 (SURVEY.md App. B)\n'
-           f'#pragma once\n\n'
+           f'#pragma once\n#ifndef RB_SCR_STRIDE\n#define RB_SCR_STRIDE 32\n#endif\n\n'
            f'struct PF_{name} {{\n'
            f'  static constexpr int NZ = {nz}, NU = {nu}, NX = {nx}, NFC = {NFC}, '
            f'NVP = {len(variant.vp_names)};\n'

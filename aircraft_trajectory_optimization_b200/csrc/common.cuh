@@ -61,4 +61,5 @@ struct RbBatch {
   double* jac;
   double* hess;
   double* fpart;   // scratch [B][N] per-interval objective terms
+  double* cell_scr;  // scratch of the shooting-cell kernels (one chunk of instances)
 };

@@ -20,7 +20,7 @@
 #include "generated/pf_drone_ypr_param_gr.cuh"
 #include "generated/pf_point_pm_global.cuh"
 #include "generated/pf_point_pm_param_gr.cuh"
-#include "rk4_cells.cuh"
+#include "rk4_cells2.cuh"
 #include "colloc_cells.cuh"
 #include "simple_rows.cuh"
 #include "kkt_blocks.cuh"
@@ -55,14 +55,16 @@ int cuda_fail(cudaError_t e, const char* what) {
 struct VariantInfo {
   const char* name;
   int nz, nu, nvp;
+  int rk4_ns;   // scratch doubles per shooting cell (Rk4Scratch<PF>::NS)
 };
+#define RB_RK4_CHUNK 64   // instances per launch pair of the shooting kernels (bounds the scratch: NS * 8 B per cell)
 const VariantInfo kVariants[] = {
-    {"drone_quat_global", PF_drone_quat_global::NZ, PF_drone_quat_global::NU, PF_drone_quat_global::NVP},
-    {"drone_quat_param_gr", PF_drone_quat_param_gr::NZ, PF_drone_quat_param_gr::NU, PF_drone_quat_param_gr::NVP},
-    {"point_pm_global", PF_point_pm_global::NZ, PF_point_pm_global::NU, PF_point_pm_global::NVP},
-    {"point_pm_param_gr", PF_point_pm_param_gr::NZ, PF_point_pm_param_gr::NU, PF_point_pm_param_gr::NVP},
-    {"drone_ypr_param_gr", PF_drone_ypr_param_gr::NZ, PF_drone_ypr_param_gr::NU, PF_drone_ypr_param_gr::NVP},
-    {"drone_ypr_global", PF_drone_ypr_global::NZ, PF_drone_ypr_global::NU, PF_drone_ypr_global::NVP},
+    {"drone_quat_global", PF_drone_quat_global::NZ, PF_drone_quat_global::NU, PF_drone_quat_global::NVP, Rk4Scratch<PF_drone_quat_global>::NS},
+    {"drone_quat_param_gr", PF_drone_quat_param_gr::NZ, PF_drone_quat_param_gr::NU, PF_drone_quat_param_gr::NVP, Rk4Scratch<PF_drone_quat_param_gr>::NS},
+    {"point_pm_global", PF_point_pm_global::NZ, PF_point_pm_global::NU, PF_point_pm_global::NVP, Rk4Scratch<PF_point_pm_global>::NS},
+    {"point_pm_param_gr", PF_point_pm_param_gr::NZ, PF_point_pm_param_gr::NU, PF_point_pm_param_gr::NVP, Rk4Scratch<PF_point_pm_param_gr>::NS},
+    {"drone_ypr_param_gr", PF_drone_ypr_param_gr::NZ, PF_drone_ypr_param_gr::NU, PF_drone_ypr_param_gr::NVP, Rk4Scratch<PF_drone_ypr_param_gr>::NS},
+    {"drone_ypr_global", PF_drone_ypr_global::NZ, PF_drone_ypr_global::NU, PF_drone_ypr_global::NVP, Rk4Scratch<PF_drone_ypr_global>::NS},
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
@@ -71,8 +73,27 @@ cudaError_t launch_cells_t(const RbDev& d, const RbBatch& b, cudaStream_t st) {
   const long long cells = (long long)b.B * d.N;
   if (d.transcription == RB_RK4) {
     constexpr int CPB = RB_CELL_THREADS / (PF::NX + 1);
-    const long long blocks = (cells + CPB - 1) / CPB;
-    rk4_cells_kernel<PF><<<(unsigned)blocks, RB_CELL_THREADS, 0, st>>>(d, b);
+    if (!b.cell_scr) return cudaErrorInvalidValue;
+    for (int p0 = 0; p0 < b.B; p0 += RB_RK4_CHUNK) {
+      RbBatch c = b;
+      c.B = b.B - p0 < RB_RK4_CHUNK ? b.B - p0 : RB_RK4_CHUNK;
+      c.x += (size_t)p0 * d.nw;
+      if (c.lam_g) c.lam_g += (size_t)p0 * d.ng;
+      if (c.lam_f) c.lam_f += p0;
+      c.vp += (size_t)p0 * b.vp_stride;
+      if (c.fc_b) c.fc_b += (size_t)p0 * d.N * PF::NFC;
+      if (c.grad_f) c.grad_f += (size_t)p0 * d.nw;
+      if (c.g) c.g += (size_t)p0 * d.ng;
+      if (c.jac) c.jac += (size_t)p0 * d.nnzj;
+      if (c.hess) c.hess += (size_t)p0 * d.nnzh;
+      if (c.fpart) c.fpart += (size_t)p0 * d.N;
+      const long long cc = (long long)c.B * d.N;
+      rk4_point_kernel<PF><<<(unsigned)((cc + 127) / 128), 128, 0, st>>>(d, c, b.cell_scr);
+      rk4_dir_kernel<PF><<<(unsigned)((cc + CPB - 1) / CPB), RB_CELL_THREADS,
+                          3 * PF::NZ * RB_CELL_THREADS * sizeof(double), st>>>(d, c, b.cell_scr);
+      g_launches += 2;
+    }
+    return cudaGetLastError();
   } else {
     const long long blocks = (cells + RB_COLLOC_WPB - 1) / RB_COLLOC_WPB;
     const size_t smem = sizeof(double) * RB_COLLOC_WPB * (size_t)colloc_cell_doubles<PF>(d.cell_nj, d.cell_nh);
@@ -302,9 +323,18 @@ int rb_sparsity_get(const rb_problem* p, int which, long long* out) {
   return 0;
 }
 
+static size_t fpart_bytes(const rb_problem* p, int B) {
+  return (((size_t)B * p->d.N * sizeof(double)) + 255) / 256 * 256;
+}
+
 size_t rb_eval_scratch_bytes(const rb_problem* p, int B) {
   if (!p || B <= 0) return 0;
-  return (size_t)B * p->d.N * sizeof(double) + 256;
+  size_t n = fpart_bytes(p, B) + 256;
+  if (p->d.transcription == RB_RK4) {
+    const long long cells = (long long)(B < RB_RK4_CHUNK ? B : RB_RK4_CHUNK) * p->d.N;
+    n += (size_t)((cells + 31) / 32) * kVariants[p->variant].rk4_ns * 32 * sizeof(double);
+  }
+  return n;
 }
 
 int rb_eval_batch(const rb_problem* p, int B, const double* x, const double* lam_g, const double* lam_f,
@@ -313,7 +343,7 @@ int rb_eval_batch(const rb_problem* p, int B, const double* x, const double* lam
   if (!p || !x || !vp) return fail("rb_eval_batch: null problem / x / vp");
   if (B <= 0) return 0;
   if (hess && !lam_g && p->d.ng > 0) return fail("rb_eval_batch: hess requested without lam_g");
-  if (f && !scratch) return fail("rb_eval_batch: f requested without scratch");
+  if ((f || p->d.transcription == RB_RK4) && !scratch) return fail("rb_eval_batch: scratch buffer required");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   RbBatch b{};
   b.B = B;
@@ -329,6 +359,7 @@ int rb_eval_batch(const rb_problem* p, int B, const double* x, const double* lam
   b.jac = jac;
   b.hess = hess;
   b.fpart = f ? static_cast<double*>(scratch) : nullptr;
+  b.cell_scr = scratch ? reinterpret_cast<double*>(static_cast<char*>(scratch) + fpart_bytes(p, B)) : nullptr;
   const RbDev& d = p->d;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (g_timer.on) {

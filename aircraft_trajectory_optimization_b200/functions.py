@@ -313,9 +313,13 @@ class NlpFunctions:
         if vp is None:
             raise ValueError('vp (device tensor) is required')
         vp_stride = 0 if vp.dim() == 1 else vp.shape[1]
-        if f is not None and scratch is None:
-            scratch = torch.empty(self.lib.rb_eval_scratch_bytes(self.handle, B), dtype=torch.uint8,
-                                  device=x.device)
+        if scratch is None:
+            need = self.lib.rb_eval_scratch_bytes(self.handle, B)
+            cached = getattr(self, '_scratch', None)
+            if cached is None or cached.numel() < need or cached.device != x.device:
+                cached = torch.empty(need, dtype=torch.uint8, device=x.device)
+                self._scratch = cached
+            scratch = cached
         if stream is None:
             stream = torch.cuda.current_stream(x.device).cuda_stream
         dp = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
