@@ -205,16 +205,16 @@ def generate_variant(variant: Variant, out_dir=GEN_DIR):
         + [f'Hst[th[{i}]]' for i in range(len(pf.W))])
     parts.append(code)
     # ---- materialised form for the two-kernel shooting path (csrc/rk4_cells.cuh) ------------------
-    # fJ_s / vjpW_s write the non-zeros of J and W straight into a strided scratch column (stride RB_SCR_STRIDE);
+    # fJ_s / vjpW_s write the non-zeros of J and W straight into a strided scratch column (stride SCR_STRIDE);
     # jmul / jtmul / wmul are the sparse products the direction threads run against those columns.
     code, ops['fJ_s'] = _emit_fn(pf, 'fJ_s', [cx, cfc, cvp, 'double* __restrict__ f', 'double* __restrict__ Js'],
                                  pf.f + pf.J_nodes,
-                                 [f'f[{i}]' for i in range(nz)] + [f'Js[{i} * RB_SCR_STRIDE]' for i in range(len(pf.J))])
+                                 [f'f[{i}]' for i in range(nz)] + [f'Js[{i} * SCR_STRIDE]' for i in range(len(pf.J))])
     parts.append(code)
     code, ops['vjpW_s'] = _emit_fn(pf, 'vjpW_s', [cx, 'const double* __restrict__ kb', cfc, cvp,
                                                   'double* __restrict__ xb', 'double* __restrict__ Ws'],
                                    pf.xb + pf.W_nodes,
-                                   [f'xb[{i}]' for i in range(nx)] + [f'Ws[{i} * RB_SCR_STRIDE]' for i in range(len(pf.W))])
+                                   [f'xb[{i}]' for i in range(nx)] + [f'Ws[{i} * SCR_STRIDE]' for i in range(len(pf.W))])
     parts.append(code)
 
     def sparse_product(fname, sig, lines_fn, nops):
@@ -224,14 +224,14 @@ def generate_variant(variant: Variant, out_dir=GEN_DIR):
     def jmul_lines():
         out = []
         for r in range(nz):
-            terms = [f'Js[{e} * RB_SCR_STRIDE] * dx[{c}]' for e, (rr, c) in enumerate(pf.J) if rr == r]
+            terms = [f'Js[{e} * SCR_STRIDE] * dx[{c}]' for e, (rr, c) in enumerate(pf.J) if rr == r]
             out.append(f'dk[{r}] = ' + (' + '.join(terms) if terms else '0.0') + ';')
         return out
 
     def jtmul_lines():
         out = []
         for c in range(nx):
-            terms = [f'Js[{e} * RB_SCR_STRIDE] * dkb[{r}]' for e, (r, cc) in enumerate(pf.J) if cc == c]
+            terms = [f'Js[{e} * SCR_STRIDE] * dkb[{r}]' for e, (r, cc) in enumerate(pf.J) if cc == c]
             if terms:
                 out.append(f'dxb[{c}] += ' + ' + '.join(terms) + ';')
         return out
@@ -242,9 +242,9 @@ def generate_variant(variant: Variant, out_dir=GEN_DIR):
             terms = []
             for e, (r, c) in enumerate(pf.W):
                 if r == i:
-                    terms.append(f'Ws[{e} * RB_SCR_STRIDE] * dx[{c}]')
+                    terms.append(f'Ws[{e} * SCR_STRIDE] * dx[{c}]')
                 elif c == i:
-                    terms.append(f'Ws[{e} * RB_SCR_STRIDE] * dx[{r}]')
+                    terms.append(f'Ws[{e} * SCR_STRIDE] * dx[{r}]')
             out.append(f'dxb[{i}] = ' + (' + '.join(terms) if terms else '0.0') + ';')
         return out
 
@@ -263,11 +263,14 @@ def generate_variant(variant: Variant, out_dir=GEN_DIR):
     hdr = (f'// GENERATED by aircraft_trajectory_optimization_b200/codegen.py -- do not edit.\n'
            f'// variant {name}: reference equations drone3d/dynamics/drone_models.py:47-123,249-292,\n'
            f'// point_model.py:28-75,149-213, rotations.py:44-102 (SURVEY.md App. B)\n'
-           f'#pragma once\n#ifndef RB_SCR_STRIDE\n#define RB_SCR_STRIDE 32\n#endif\n\n'
+           f'#pragma once\n\n'
            f'struct PF_{name} {{\n'
            f'  static constexpr int NZ = {nz}, NU = {nu}, NX = {nx}, NFC = {NFC}, '
            f'NVP = {len(variant.vp_names)};\n'
            f'  static constexpr int NJ = {len(pf.J)}, NW = {len(pf.W)};\n'
+           f'  // shooting cells: CPB cells per 128-thread block of the direction kernel; the scratch of a block is\n'
+           f'  // stored entry-major with the CPB cells of the block adjacent (stride of one entry = CPB doubles)\n'
+           f'  static constexpr int CPB = 128 / ({nx} + 1), SCR_STRIDE = CPB;\n'
            f'  static constexpr bool QUAT = {"true" if variant.vehicle == "drone" and variant.orient == "quat" else "false"};\n'
            f'  static constexpr bool USES_FC = {"true" if variant.parametric else "false"};\n'
            + table('J_ROW', [r for r, _ in pf.J]) + table('J_COL', [c for _, c in pf.J])

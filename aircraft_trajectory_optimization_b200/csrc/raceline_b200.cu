@@ -56,15 +56,19 @@ struct VariantInfo {
   const char* name;
   int nz, nu, nvp;
   int rk4_ns;   // scratch doubles per shooting cell (Rk4Scratch<PF>::NS)
+  int rk4_cpb;  // cells per CTA of the direction kernel (scratch group size)
 };
-#define RB_RK4_CHUNK 64   // instances per launch pair of the shooting kernels (bounds the scratch: NS * 8 B per cell)
+#ifndef RB_RK4_CHUNK
+#define RB_RK4_CHUNK 64
+#endif
+//   // instances per launch pair of the shooting kernels (bounds the scratch: NS * 8 B per cell)
 const VariantInfo kVariants[] = {
-    {"drone_quat_global", PF_drone_quat_global::NZ, PF_drone_quat_global::NU, PF_drone_quat_global::NVP, Rk4Scratch<PF_drone_quat_global>::NS},
-    {"drone_quat_param_gr", PF_drone_quat_param_gr::NZ, PF_drone_quat_param_gr::NU, PF_drone_quat_param_gr::NVP, Rk4Scratch<PF_drone_quat_param_gr>::NS},
-    {"point_pm_global", PF_point_pm_global::NZ, PF_point_pm_global::NU, PF_point_pm_global::NVP, Rk4Scratch<PF_point_pm_global>::NS},
-    {"point_pm_param_gr", PF_point_pm_param_gr::NZ, PF_point_pm_param_gr::NU, PF_point_pm_param_gr::NVP, Rk4Scratch<PF_point_pm_param_gr>::NS},
-    {"drone_ypr_param_gr", PF_drone_ypr_param_gr::NZ, PF_drone_ypr_param_gr::NU, PF_drone_ypr_param_gr::NVP, Rk4Scratch<PF_drone_ypr_param_gr>::NS},
-    {"drone_ypr_global", PF_drone_ypr_global::NZ, PF_drone_ypr_global::NU, PF_drone_ypr_global::NVP, Rk4Scratch<PF_drone_ypr_global>::NS},
+    {"drone_quat_global", PF_drone_quat_global::NZ, PF_drone_quat_global::NU, PF_drone_quat_global::NVP, Rk4Scratch<PF_drone_quat_global>::NS, PF_drone_quat_global::CPB},
+    {"drone_quat_param_gr", PF_drone_quat_param_gr::NZ, PF_drone_quat_param_gr::NU, PF_drone_quat_param_gr::NVP, Rk4Scratch<PF_drone_quat_param_gr>::NS, PF_drone_quat_param_gr::CPB},
+    {"point_pm_global", PF_point_pm_global::NZ, PF_point_pm_global::NU, PF_point_pm_global::NVP, Rk4Scratch<PF_point_pm_global>::NS, PF_point_pm_global::CPB},
+    {"point_pm_param_gr", PF_point_pm_param_gr::NZ, PF_point_pm_param_gr::NU, PF_point_pm_param_gr::NVP, Rk4Scratch<PF_point_pm_param_gr>::NS, PF_point_pm_param_gr::CPB},
+    {"drone_ypr_param_gr", PF_drone_ypr_param_gr::NZ, PF_drone_ypr_param_gr::NU, PF_drone_ypr_param_gr::NVP, Rk4Scratch<PF_drone_ypr_param_gr>::NS, PF_drone_ypr_param_gr::CPB},
+    {"drone_ypr_global", PF_drone_ypr_global::NZ, PF_drone_ypr_global::NU, PF_drone_ypr_global::NVP, Rk4Scratch<PF_drone_ypr_global>::NS, PF_drone_ypr_global::CPB},
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
@@ -74,6 +78,13 @@ cudaError_t launch_cells_t(const RbDev& d, const RbBatch& b, cudaStream_t st) {
   if (d.transcription == RB_RK4) {
     constexpr int CPB = RB_CELL_THREADS / (PF::NX + 1);
     if (!b.cell_scr) return cudaErrorInvalidValue;
+    const size_t dir_smem = (2 * (size_t)Rk4Scratch<PF>::STAGE_DOUBLES + 3 * PF::NZ * RB_CELL_THREADS) * sizeof(double);
+    static bool configured_dir = false;
+    if (!configured_dir) {
+      cudaError_t e = cudaFuncSetAttribute(rk4_dir_kernel<PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dir_smem);
+      if (e != cudaSuccess) return e;
+      configured_dir = true;
+    }
     for (int p0 = 0; p0 < b.B; p0 += RB_RK4_CHUNK) {
       RbBatch c = b;
       c.B = b.B - p0 < RB_RK4_CHUNK ? b.B - p0 : RB_RK4_CHUNK;
@@ -89,8 +100,7 @@ cudaError_t launch_cells_t(const RbDev& d, const RbBatch& b, cudaStream_t st) {
       if (c.fpart) c.fpart += (size_t)p0 * d.N;
       const long long cc = (long long)c.B * d.N;
       rk4_point_kernel<PF><<<(unsigned)((cc + 127) / 128), 128, 0, st>>>(d, c, b.cell_scr);
-      rk4_dir_kernel<PF><<<(unsigned)((cc + CPB - 1) / CPB), RB_CELL_THREADS,
-                          3 * PF::NZ * RB_CELL_THREADS * sizeof(double), st>>>(d, c, b.cell_scr);
+      rk4_dir_kernel<PF><<<(unsigned)((cc + CPB - 1) / CPB), RB_CELL_THREADS, dir_smem, st>>>(d, c, b.cell_scr);
       g_launches += 2;
     }
     return cudaGetLastError();
@@ -332,7 +342,8 @@ size_t rb_eval_scratch_bytes(const rb_problem* p, int B) {
   size_t n = fpart_bytes(p, B) + 256;
   if (p->d.transcription == RB_RK4) {
     const long long cells = (long long)(B < RB_RK4_CHUNK ? B : RB_RK4_CHUNK) * p->d.N;
-    n += (size_t)((cells + 31) / 32) * kVariants[p->variant].rk4_ns * 32 * sizeof(double);
+    const int cpb = kVariants[p->variant].rk4_cpb;
+    n += (size_t)((cells + cpb - 1) / cpb) * kVariants[p->variant].rk4_ns * cpb * sizeof(double);
   }
   return n;
 }

@@ -6,31 +6,32 @@
 // reuse the last interval's step), drone3d/raceline/base_raceline.py:601-623 (stage cost * h).
 //
 //   rk4_point_kernel : one thread per (instance, interval).  Runs the primal RK4 chain and the primal
-//                      adjoint chain of mu' out once, and writes per stage i = 1..4 the non-zeros of
-//                      J_i = df/dx(X_i), of W_i = sum_c kb_i[c] d2f_c/dx2(X_i), the slope k_i and the
-//                      adjoint xb_i = J_i' kb_i into a scratch column (entry e of cell c at
-//                      scr[(c / 32 * NS + e) * 32 + c % 32]: coalesced for this kernel, and the 32 cells a
-//                      warp of the second kernel touches share cache lines).
-//   rk4_dir_kernel   : one thread per (instance, interval, direction v_col of (z, u, h)).  Pushes e_col
-//                      through the four stages with sparse products against the stored J_i (Jacobian column)
+//                      adjoint chain of mu' out once and writes, per stage i = 1..4, the non-zeros of
+//                      J_i = df/dx(X_i) and W_i = sum_c kb_i[c] d2f_c/dx2(X_i), the slopes k_i, k_{i-1} and the
+//                      adjoints xb_i = J_i' kb_i, xb_{i+1} into scratch.
+//   rk4_dir_kernel   : one thread per (instance, interval, direction v_col of (z, u, h)), CPB cells per CTA.
+//                      Pushes e_col through the four stages with sparse products against J_i (Jacobian column)
 //                      and pulls the tangent of the adjoint sweep back with W_i dX_i + J_i' dkb_i (Hessian
-//                      column); then the same epilogue as before: rows, objective pieces, CCS slot writes.
+//                      column); then rows, objective pieces and the CCS slot writes.
 //
-// The straight-line point functions (fJ_s, vjpW_s) therefore run once per cell instead of once per direction,
-// and the per-direction work is ~1.3 k multiply-adds against L1-resident operands.
+// Scratch layout: the CPB cells of one direction-kernel CTA form a group; per group 4 stage blocks of
+// SB * CPB doubles, entry-major with the cells of the group adjacent.  A stage block is one contiguous,
+// 16-byte aligned span, so the direction kernel fetches the eight blocks it needs (stages 1..4 forward, 4..1
+// backward) with one TMA bulk copy each (cp.async.bulk + mbarrier), double-buffered in shared memory one step
+// ahead of the arithmetic; all ~1.3 k operand reads of a thread are then short-latency shared-memory reads.
 #pragma once
 #include "common.cuh"
 
 template <class PF>
 struct Rk4Scratch {
-  static constexpr int NZ = PF::NZ, NJ = PF::NJ, NW = PF::NW;
-  static constexpr int SS = NJ + NW + 2 * NZ;     // per stage: J, W, k, xb(z part)
-  static constexpr int NS = 4 * SS;
-  __host__ __device__ static constexpr int oJ(int i) { return i * SS; }
-  __host__ __device__ static constexpr int oW(int i) { return i * SS + NJ; }
-  __host__ __device__ static constexpr int oK(int i) { return i * SS + NJ + NW; }
-  __host__ __device__ static constexpr int oX(int i) { return i * SS + NJ + NW + NZ; }
-  __host__ __device__ static size_t doubles(long long cells) { return (size_t)((cells + 31) / 32) * NS * 32; }
+  static constexpr int NZ = PF::NZ, NJ = PF::NJ, NW = PF::NW, CPB = PF::CPB;
+  // entries of a stage block: J, W, k_i, xb_i (z part), k_{i-1}, xb_{i+1} (z part); padded to an even count so
+  // that SB * CPB * 8 bytes is a multiple of 16 (TMA bulk copies)
+  static constexpr int oJ = 0, oW = NJ, oK = NJ + NW, oX = oK + NZ, oKp = oX + NZ, oXn = oKp + NZ;
+  static constexpr int SB = (oXn + NZ + 1) / 2 * 2;
+  static constexpr int NS = 4 * SB;                  // doubles per cell
+  static constexpr int STAGE_DOUBLES = SB * CPB;     // doubles per (group, stage) block
+  __host__ __device__ static size_t doubles(long long cells) { return (size_t)((cells + CPB - 1) / CPB) * NS * CPB; }
 };
 
 // multipliers of the cell's state rows pulled through cont(): muz = d(mu' cont(zn)) / d zn
@@ -59,7 +60,7 @@ template <class PF>
 __global__ void __launch_bounds__(128)
 rk4_point_kernel(const RbDev d, const RbBatch b, double* __restrict__ scr) {
   using SC = Rk4Scratch<PF>;
-  constexpr int NZ = PF::NZ, NU = PF::NU, NX = PF::NX, NR = NZ + NU;
+  constexpr int NZ = PF::NZ, NU = PF::NU, NX = PF::NX, NR = NZ + NU, CPB = SC::CPB;
   const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (cell >= (long long)b.B * d.N) return;
   const int p = (int)(cell / d.N);
@@ -70,7 +71,8 @@ rk4_point_kernel(const RbDev d, const RbBatch b, double* __restrict__ scr) {
   const double* __restrict__ fcp =
       PF::USES_FC ? (b.fc_b ? b.fc_b + (size_t)p * d.N * PF::NFC : d.fc) + (size_t)n * PF::NFC : d.fc;
   const double* __restrict__ vpp = b.vp + (size_t)p * b.vp_stride;
-  double* __restrict__ S = scr + ((size_t)(cell >> 5) * SC::NS) * 32 + (cell & 31);
+  // entry e of stage st of this cell: S[(st * SB + e) * CPB]
+  double* __restrict__ S = scr + (size_t)(cell / CPB) * SC::NS * CPB + (cell % CPB);
 
   double x1[NX], xs[NX], k[NZ], Ks[NZ];
 #pragma unroll
@@ -79,17 +81,22 @@ rk4_point_kernel(const RbDev d, const RbBatch b, double* __restrict__ scr) {
     xs[i] = x1[i];
   }
 #pragma unroll
-  for (int i = 0; i < NZ; ++i) Ks[i] = 0.0;
+  for (int i = 0; i < NZ; ++i) {
+    Ks[i] = 0.0;
+    k[i] = 0.0;
+  }
   // ---- primal chain: k_i = f(X_i), J_i;  X_{i+1} = x + a_{i+1} h k_i,  a = (0, 1/2, 1/2, 1),  b = (1, 2, 2, 1)
 #pragma unroll 1
   for (int st = 0; st < 4; ++st) {
-    double* __restrict__ Sst = S + (size_t)st * SC::SS * 32;
-    PF::fJ_s(xs, fcp, vpp, k, Sst);
+    double* __restrict__ Sst = S + (size_t)st * SC::SB * CPB;
+#pragma unroll
+    for (int i = 0; i < NZ; ++i) Sst[(SC::oKp + i) * CPB] = k[i];          // k_{st-1} (zero for the first stage)
+    PF::fJ_s(xs, fcp, vpp, k, Sst + SC::oJ * CPB);
     const double bw = (st == 0 || st == 3) ? 1.0 : 2.0;
-    const double an = (st == 2) ? h : 0.5 * h;        // a_{st+1} h
+    const double an = (st == 2) ? h : 0.5 * h;        // a_{st+2} h
 #pragma unroll
     for (int i = 0; i < NZ; ++i) {
-      Sst[(SC::NJ + SC::NW + i) * 32] = k[i];
+      Sst[(SC::oK + i) * CPB] = k[i];
       Ks[i] += bw * k[i];
       if (st < 3) xs[i] = x1[i] + an * k[i];
     }
@@ -107,35 +114,84 @@ rk4_point_kernel(const RbDev d, const RbBatch b, double* __restrict__ scr) {
   for (int i = 0; i < NX; ++i) xb[i] = 0.0;
 #pragma unroll 1
   for (int st = 3; st >= 0; --st) {
-    double* __restrict__ Sst = S + (size_t)st * SC::SS * 32;
+    double* __restrict__ Sst = S + (size_t)st * SC::SB * CPB;
     const double bw = (st == 0 || st == 3) ? h6 : 2.0 * h6;
     const double an = (st == 3) ? 0.0 : ((st == 2) ? h : 0.5 * h);     // a_{st+2} h (coefficient of xb_{st+1})
     const double ax = (st == 0) ? 0.0 : ((st == 3) ? h : 0.5 * h);     // a_{st+1} h (X_st = x + ax k_{st-1})
 #pragma unroll
     for (int i = 0; i < NZ; ++i) {
+      Sst[(SC::oXn + i) * CPB] = xb[i];                                  // xb_{st+1} (zero for the last stage)
       kb[i] = bw * muz[i] + an * xb[i];
-      xs[i] = x1[i] + (st > 0 ? ax * Sst[((long long)(SC::NJ + SC::NW + i) - SC::SS) * 32] : 0.0);
+      xs[i] = x1[i] + ax * Sst[(SC::oKp + i) * CPB];
     }
-    PF::vjpW_s(xs, kb, fcp, vpp, xb, Sst + SC::NJ * 32);
+    PF::vjpW_s(xs, kb, fcp, vpp, xb, Sst + SC::oW * CPB);
 #pragma unroll
-    for (int i = 0; i < NZ; ++i) Sst[(SC::NJ + SC::NW + NZ + i) * 32] = xb[i];
+    for (int i = 0; i < NZ; ++i) Sst[(SC::oX + i) * CPB] = xb[i];
   }
 }
 
+#ifndef RB_DIR_MINBLOCKS
+#define RB_DIR_MINBLOCKS 3
+#endif
 template <class PF>
-__global__ void __launch_bounds__(RB_CELL_THREADS)
+__global__ void __launch_bounds__(RB_CELL_THREADS, RB_DIR_MINBLOCKS)
 rk4_dir_kernel(const RbDev d, const RbBatch b, const double* __restrict__ scr) {
   using SC = Rk4Scratch<PF>;
   constexpr int NZ = PF::NZ, NU = PF::NU, NX = PF::NX, NV = NX + 1, NL = NV + NU, NR = NZ + NU;
-  constexpr int CPB = RB_CELL_THREADS / NV;
+  constexpr int CPB = SC::CPB;
+  static_assert(CPB == RB_CELL_THREADS / NV, "cells per CTA");
+  constexpr unsigned STAGE_BYTES = SC::STAGE_DOUBLES * sizeof(double);
+  static_assert(STAGE_BYTES % 16 == 0, "TMA bulk copies move multiples of 16 bytes");
+  // shared memory: two stage buffers (TMA destinations), then [3 NZ][RB_CELL_THREADS] thread-private tangents
+  extern __shared__ __align__(128) double rk4_smem[];
+  __shared__ __align__(8) unsigned long long rk4_bar[2];
+  double* __restrict__ dks = rk4_smem + 2 * SC::STAGE_DOUBLES + (size_t)threadIdx.x;
+  const double* __restrict__ grp = scr + (size_t)blockIdx.x * SC::NS * CPB;     // this CTA's group
+  // step s = 0..7 reads stage (s < 4 ? s : 7 - s) from buffer s & 1
+  auto issue = [&](int step) {
+    const int stg = step < 4 ? step : 7 - step;
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&rk4_bar[step & 1]);
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(rk4_smem + (size_t)(step & 1) * SC::STAGE_DOUBLES);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(STAGE_BYTES) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(grp + (size_t)stg * SC::STAGE_DOUBLES), "r"(STAGE_BYTES), "r"(bar)
+                 : "memory");
+  };
+  auto wait = [&](int step) {
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&rk4_bar[step & 1]);
+    const unsigned parity = (step >> 1) & 1;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "RK4_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra RK4_DONE_%=;\n"
+        "bra RK4_WAIT_%=;\n"
+        "RK4_DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+  };
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&rk4_bar[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&rk4_bar[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const bool want_h = b.hess != nullptr;
+  const int nsteps = want_h ? 8 : 4;
+  if (threadIdx.x == 0) {
+    issue(0);
+    issue(1);
+  }
   const int lc = threadIdx.x / NV;
   const int col = threadIdx.x - lc * NV;
-  if (lc >= CPB) return;
   const long long cell = (long long)blockIdx.x * CPB + lc;
-  if (cell >= (long long)b.B * d.N) return;
-  const int p = (int)(cell / d.N);
-  const int n = (int)(cell - (long long)p * d.N);
-  const double* __restrict__ S = scr + ((size_t)(cell >> 5) * SC::NS) * 32 + (cell & 31);
+  // threads without a cell still take part in the barriers of the pipeline
+  const bool live = lc < CPB && cell < (long long)b.B * d.N;
+  const long long cell_c = live ? cell : 0;
+  const int p = (int)(cell_c / d.N);
+  const int n = (int)(cell_c - (long long)p * d.N);
 
   const double* __restrict__ w = b.x + (size_t)p * d.nw;
   const double h = w[n];
@@ -153,8 +209,7 @@ rk4_dir_kernel(const RbDev d, const RbBatch b, const double* __restrict__ scr) {
   // ---------------------------------------------------------------- forward sweep: dk_i = J_i dX_i
   // dX_i = e + a_i (h dk_{i-1} + dh k_{i-1}),  a = (0, 1/2, 1/2, 1);  dk_1..dk_3 are kept in this thread's
   // shared-memory slots for the reverse sweep
-  extern __shared__ double rk4_smem[];
-  double* __restrict__ dks = rk4_smem + (size_t)threadIdx.x;     // dks[(st * NZ + i) * RB_CELL_THREADS]
+  const int lcs = live ? lc : 0;
   const double h6 = h / 6.0, dh6 = dh / 6.0;
   double dxs[NX], dk[NZ], Ks[NZ], dKs[NZ];
 #pragma unroll
@@ -166,13 +221,14 @@ rk4_dir_kernel(const RbDev d, const RbBatch b, const double* __restrict__ scr) {
   }
 #pragma unroll 1
   for (int st = 0; st < 4; ++st) {
-    const double* __restrict__ Sst = S + (size_t)st * SC::SS * 32;
-    PF::jmul(Sst, dxs, dk);
+    wait(st);
+    const double* __restrict__ Sst = rk4_smem + (size_t)(st & 1) * SC::STAGE_DOUBLES + lcs;
+    PF::jmul(Sst + SC::oJ * CPB, dxs, dk);
     const double bw = (st == 0 || st == 3) ? 1.0 : 2.0;
     const double an = (st == 2) ? 1.0 : 0.5;
 #pragma unroll
     for (int i = 0; i < NZ; ++i) {
-      const double ki = Sst[(SC::NJ + SC::NW + i) * 32];
+      const double ki = Sst[(SC::oK + i) * CPB];
       Ks[i] += bw * ki;
       dKs[i] += bw * dk[i];
       if (st < 3) {
@@ -180,6 +236,8 @@ rk4_dir_kernel(const RbDev d, const RbBatch b, const double* __restrict__ scr) {
         dxs[i] = e[i] + an * (h * dk[i] + dh * ki);
       }
     }
+    __syncthreads();                                  // everyone is done with this buffer
+    if (threadIdx.x == 0 && st + 2 < nsteps) issue(st + 2);
   }
   double zn[NZ], dzn[NZ];
 #pragma unroll
@@ -236,7 +294,7 @@ rk4_dir_kernel(const RbDev d, const RbBatch b, const double* __restrict__ scr) {
   }
 
   // ---------------------------------------------------------------- g, jac_g
-  if (b.g || b.jac) {
+  if (live && (b.g || b.jac)) {
     double* __restrict__ g = b.g ? b.g + (size_t)p * d.ng : nullptr;
     double* __restrict__ jac = b.jac ? b.jac + (size_t)p * d.nnzj : nullptr;
     const int32_t* __restrict__ js = d.cell_jslot + (size_t)n * d.cell_nj;
@@ -294,7 +352,8 @@ rk4_dir_kernel(const RbDev d, const RbBatch b, const double* __restrict__ scr) {
 
   // ---------------------------------------------------------------- objective pieces
   const double sig = b.lam_f ? b.lam_f[p] : 1.0;
-  if (col >= NZ && col < NX) {
+  if (!live) {
+  } else if (col >= NZ && col < NX) {
     const int j = col - NZ;
     double uj = 0.0, duj = 0.0;
 #pragma unroll
@@ -317,7 +376,7 @@ rk4_dir_kernel(const RbDev d, const RbBatch b, const double* __restrict__ scr) {
     if (b.fpart) b.fpart[(size_t)p * d.N + n] = stage * h;
   }
 
-  if (!b.hess) return;
+  if (!want_h) return;
 
   // ---------------------------------------------------------------- reverse sweep: dxb_i = W_i dX_i + J_i' dkb_i
   // kb_i = (b_i h / 6) muz + a_{i+1} h xb_{i+1};  dkb_i is its tangent;  hbar gathers a_i (dxb_i . k_{i-1} + xb_i . dk_{i-1})
@@ -335,39 +394,37 @@ rk4_dir_kernel(const RbDev d, const RbBatch b, const double* __restrict__ scr) {
   for (int i = 0; i < NX; ++i) dxb[i] = 0.0;
 #pragma unroll 1
   for (int st = 3; st >= 0; --st) {
-    const double* __restrict__ Sst = S + (size_t)st * SC::SS * 32;
+    const int step = 7 - st;
+    wait(step);
+    const double* __restrict__ Sst = rk4_smem + (size_t)(step & 1) * SC::STAGE_DOUBLES + lcs;
     const double bw = (st == 0 || st == 3) ? 1.0 / 6.0 : 1.0 / 3.0;
     const double an = (st == 3) ? 0.0 : ((st == 2) ? 1.0 : 0.5);       // a_{st+2}: coefficient of (xb, dxb) of stage st+1
     const double ax = (st == 0) ? 0.0 : ((st == 3) ? 1.0 : 0.5);       // a_{st+1}: X_st = x + ax h k_{st-1}
 #pragma unroll
-    for (int i = 0; i < NZ; ++i) {
-      const double xbn = (st < 3) ? Sst[((long long)(SC::NJ + SC::NW + NZ + i) + SC::SS) * 32] : 0.0;   // xb_{st+1}
-      dkb[i] = bw * (dh * muz[i] + h * dmuz[i]) + an * (dh * xbn + h * dxb[i]);
-    }
+    for (int i = 0; i < NZ; ++i)
+      dkb[i] = bw * (dh * muz[i] + h * dmuz[i]) + an * (dh * Sst[(SC::oXn + i) * CPB] + h * dxb[i]);
 #pragma unroll
     for (int i = 0; i < NX; ++i) dxs[i] = e[i];
     if (st > 0) {
 #pragma unroll
-      for (int i = 0; i < NZ; ++i) {
-        const double kp = Sst[((long long)(SC::NJ + SC::NW + i) - SC::SS) * 32];                          // k_{st-1}
-        dxs[i] = e[i] + ax * (h * dks[((st - 1) * NZ + i) * RB_CELL_THREADS] + dh * kp);
-      }
+      for (int i = 0; i < NZ; ++i)
+        dxs[i] = e[i] + ax * (h * dks[((st - 1) * NZ + i) * RB_CELL_THREADS] + dh * Sst[(SC::oKp + i) * CPB]);
     }
-    PF::wmul(Sst + SC::NJ * 32, dxs, dxb);
-    PF::jtmul(Sst, dkb, dxb);
+    PF::wmul(Sst + SC::oW * CPB, dxs, dxb);
+    PF::jtmul(Sst + SC::oJ * CPB, dkb, dxb);
 #pragma unroll
     for (int i = 0; i < NZ; ++i) gz[i] += dxb[i];
 #pragma unroll
     for (int j = 0; j < NU; ++j) gu[j] += dxb[NZ + j];
     if (st > 0) {
 #pragma unroll
-      for (int i = 0; i < NZ; ++i) {
-        const double kp = Sst[((long long)(SC::NJ + SC::NW + i) - SC::SS) * 32];
-        const double xbi = Sst[(SC::NJ + SC::NW + NZ + i) * 32];
-        dhb += ax * (dxb[i] * kp + xbi * dks[((st - 1) * NZ + i) * RB_CELL_THREADS]);
-      }
+      for (int i = 0; i < NZ; ++i)
+        dhb += ax * (dxb[i] * Sst[(SC::oKp + i) * CPB] + Sst[(SC::oX + i) * CPB] * dks[((st - 1) * NZ + i) * RB_CELL_THREADS]);
     }
+    __syncthreads();
+    if (threadIdx.x == 0 && step + 2 < 8) issue(step + 2);
   }
+  if (!live) return;
 
   // ---------------------------------------------------------------- hess_l column `col`
   double* __restrict__ H = b.hess + (size_t)p * d.nnzh;

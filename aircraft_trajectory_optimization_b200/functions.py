@@ -18,7 +18,7 @@ from .models import vehicle_params
 from .structure import NLPStructure
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libraceline_b200.so')
+LIB_PATH = os.environ.get('RACELINE_B200_LIB') or os.path.join(_HERE, 'libraceline_b200.so')   # override: kernel experiments
 _LIB = None
 
 _c_int_p = ctypes.POINTER(ctypes.c_int32)
