@@ -59,7 +59,7 @@ struct VariantInfo {
   int rk4_cpb;  // cells per CTA of the direction kernel (scratch group size)
 };
 #ifndef RB_RK4_CHUNK
-#define RB_RK4_CHUNK 64
+#define RB_RK4_CHUNK 128
 #endif
 //   // instances per launch pair of the shooting kernels (bounds the scratch: NS * 8 B per cell)
 const VariantInfo kVariants[] = {

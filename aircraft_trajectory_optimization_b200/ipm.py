@@ -89,6 +89,7 @@ class IpmResult:
     t_kkt: float = 0.0
     t_total: float = 0.0
     history: list = field(default_factory=list)
+    factorisations_each: np.ndarray = None     # KKT factorisations every instance took part in
 
 
 def _inf_norm(t):
@@ -202,19 +203,28 @@ class InteriorPoint:
         def infeas(gv, ss):
             return torch.where(eq, gv - ceq, gv - ss)
 
-        def errors(ev_, xx, ss, yy, zL_, zU_, vL_, vU_, mu_):
-            dL, dU, eL, eU = slacks(xx, ss)
+        def error_parts(ev_, xx, ss, yy, zL_, zU_, vL_, vU_):
+            ''' the mu-independent pieces of IPOPT's scaled optimality error (one J'y product) '''
             gradL_x = ev_['grad_f'] + jt_y(ev_['jac'], yy) - zL_ + zU_
             gradL_s = torch.where(ineq, -yy - vL_ + vU_, torch.zeros_like(yy))
-            c = infeas(ev_['g'], ss)
-            comp = torch.stack([_inf_norm((dL * zL_ - mu_[:, None]) * fL), _inf_norm((dU * zU_ - mu_[:, None]) * fU),
-                                _inf_norm((eL * vL_ - mu_[:, None]) * sfL), _inf_norm((eU * vU_ - mu_[:, None]) * sfU)]).amax(0)
             zsum = (zL_ * fL + zU_ * fU).sum(1) + (vL_ * sfL + vU_ * sfU).sum(1)
             n_tot = n + int(ineq[0].sum())
             s_d = torch.clamp((yy.abs().sum(1) + zsum) / max(1, m + n_tot), min=o.s_max) / o.s_max
             s_c = torch.clamp(zsum / torch.clamp(n_bounds, min=1.0), min=o.s_max) / o.s_max
             dual = torch.maximum(_inf_norm(gradL_x), _inf_norm(gradL_s))
-            return torch.stack([dual / s_d, _inf_norm(c), comp / s_c]).amax(0), dual, _inf_norm(c), comp
+            prim = _inf_norm(infeas(ev_['g'], ss))
+            dL, dU, eL, eU = slacks(xx, ss)
+            prods = (dL * zL_ * fL, dU * zU_ * fU, eL * vL_ * sfL, eU * vU_ * sfU)
+            return dual, prim, s_d, s_c, prods
+
+        def error_at(parts, mu_):
+            dual, prim, s_d, s_c, prods = parts
+            mc = mu_[:, None]
+            comp = torch.stack([_inf_norm((pr - mc * f_)) for pr, f_ in zip(prods, (fL, fU, sfL, sfU))]).amax(0)
+            return torch.stack([dual / s_d, prim, comp / s_c]).amax(0), dual, prim, comp
+
+        def errors(ev_, xx, ss, yy, zL_, zU_, vL_, vU_, mu_):
+            return error_at(error_parts(ev_, xx, ss, yy, zL_, zU_, vL_, vU_), mu_)
 
         # ---- state -------------------------------------------------------------------------------------
         F = o.filter_size
@@ -228,6 +238,11 @@ class InteriorPoint:
         filt_phi[:, 0] = -float('inf')
         filt_n[:] = 1
         delta_w_last = torch.zeros(B, dtype=dt, device=dev)
+        delta_w = torch.zeros(B, dtype=dt, device=dev)
+        delta_c = torch.zeros(B, dtype=dt, device=dev)
+        first_try = torch.ones(B, dtype=torch.bool, device=dev)
+        attempts = torch.zeros(B, dtype=torch.long, device=dev)
+        n_fact = torch.zeros(B, dtype=torch.long, device=dev)
         status = torch.full((B,), -1, dtype=torch.long, device=dev)      # -1 iterating, -2 pending, >= 0 finished
         if 0 < o.window < B:
             status[o.window:] = -2
@@ -247,7 +262,8 @@ class InteriorPoint:
         while True:
             active = status == -1
             # ---- convergence and barrier update --------------------------------------------------------
-            E0, dual0, prim0, comp0 = errors(ev, x, s, y, zL, zU, vL, vU, torch.zeros_like(mu))
+            parts = error_parts(ev, x, s, y, zL, zU, vL, vU)
+            E0, dual0, prim0, comp0 = error_at(parts, torch.zeros_like(mu))
             done = active & (E0 <= o.tol)
             status[done] = 0
             acc = active & ~done & (E0 <= o.acceptable_tol)
@@ -272,7 +288,7 @@ class InteriorPoint:
             if n_act == 0:
                 break
             for _ in range(4):
-                Emu = errors(ev, x, s, y, zL, zU, vL, vU, mu)[0]
+                Emu = error_at(parts, mu)[0]
                 upd = active & (Emu <= o.kappa_eps * mu) & (mu > mu_floor)
                 if not bool(upd.any()):
                     break
@@ -295,54 +311,44 @@ class InteriorPoint:
             r_s = torch.where(ineq, gphi_s - y, torch.zeros_like(s))
             c = infeas(ev['g'], s)
 
-            delta_w = torch.zeros(B, dtype=dt, device=dev)
-            delta_c = torch.zeros(B, dtype=dt, device=dev)
-            need = active.clone()
-            dx = torch.zeros_like(x)
-            ds = torch.zeros_like(s)
-            dy = torch.zeros_like(y)
-            first_try = torch.ones(B, dtype=torch.bool, device=dev)
-            for attempt in range(40):
-                dw_c = delta_w[:, None]
-                Ss_reg = torch.where(ineq, Ss + dw_c, torch.ones_like(Ss))
-                negd = torch.where(ineq, -1.0 / Ss_reg, torch.zeros_like(Ss)) - delta_c[:, None]
-                rhs = torch.cat([-r_x, torch.where(ineq, -c - r_s / Ss_reg, -c)], dim=1)
-                sol, st = kkt(ev['hess'], ev['jac'], Sx + dw_c, negd, rhs, need)
-                if o.verbose and attempt >= 1:
-                    print(f'        attempt {attempt}: dw={float(delta_w[0]):.2e} dc={float(delta_c[0]):.2e} bad_piv={int(st[0, 0])} neg={int(st[0, 1])} (want {m})')
-                dx_t, dy_t = sol[:, :n], sol[:, n:]
-                ds_t = torch.where(ineq, (dy_t - r_s) / Ss_reg, torch.zeros_like(s))
-                finite = torch.isfinite(sol).all(1)
-                singular = (st[:, 0] != 0) | ~finite
-                wrong_inertia = st[:, 1] != m
-                bad = need & (singular | wrong_inertia)
-                good = need & ~bad
-                dx = torch.where(good[:, None], dx_t, dx)
-                dy = torch.where(good[:, None], dy_t, dy)
-                ds = torch.where(good[:, None], ds_t, ds)
-                delta_w_last = torch.where(good & (delta_w > 0), delta_w, delta_w_last)
-                need = bad
-                if not bool(need.any()):
-                    break
-                # too few negative eigenvalues or a vanishing pivot: the constraint Jacobian is (numerically)
-                # rank deficient -> perturb the constraint block first and retry with the same delta_w
-                degenerate = need & (singular | (st[:, 1] < m)) & (delta_c == 0)
-                delta_c = torch.where(degenerate, o.delta_c_bar * mu ** o.kappa_c, delta_c)
-                esc = need & ~degenerate
-                # IPOPT's escalation schedule for delta_w (Algorithm IC)
-                start = torch.where(delta_w_last == 0, torch.full_like(delta_w, o.delta_w_first),
-                                    torch.clamp(o.kappa_w_minus * delta_w_last, min=o.delta_w_min))
-                grow = torch.where(delta_w_last == 0, o.kappa_w_plus_first * delta_w, o.kappa_w_plus * delta_w)
-                delta_w = torch.where(esc, torch.where(first_try, start, grow), delta_w)
-                first_try = first_try & ~esc
-                hopeless = need & (delta_w > o.delta_w_max)
-                status[hopeless] = 3
-                need = need & ~hopeless
-                if not bool(need.any()):
-                    break
-            active = status == -1
-            am = active[:, None]
-            dx, ds, dy = dx * am, ds * am, dy * am
+            # One factorisation call per sweep (IPOPT's Algorithm IC, de-serialised over the batch): an instance
+            # whose KKT matrix has the wrong inertia does not step in this sweep; it keeps its iterate, escalates
+            # its own (delta_w, delta_c) and is factorised again together with everybody else in the next sweep.
+            dw_c = delta_w[:, None]
+            Ss_reg = torch.where(ineq, Ss + dw_c, torch.ones_like(Ss))
+            negd = torch.where(ineq, -1.0 / Ss_reg, torch.zeros_like(Ss)) - delta_c[:, None]
+            rhs = torch.cat([-r_x, torch.where(ineq, -c - r_s / Ss_reg, -c)], dim=1)
+            sol, st = kkt(ev['hess'], ev['jac'], Sx + dw_c, negd, rhs, active)
+            n_fact = n_fact + active.long()
+            if o.verbose:
+                print(f'        dw={float(delta_w[0]):.2e} dc={float(delta_c[0]):.2e} bad_piv={int(st[0, 0])} '
+                      f'neg={int(st[0, 1])} (want {m}) attempt {int(attempts[0])}')
+            finite = torch.isfinite(sol).all(1)
+            singular = (st[:, 0] != 0) | ~finite
+            wrong_inertia = st[:, 1] != m
+            bad = active & (singular | wrong_inertia)
+            moved = active & ~bad
+            mv = moved[:, None]
+            dx = torch.where(mv, sol[:, :n], torch.zeros_like(x))
+            dy = torch.where(mv, sol[:, n:], torch.zeros_like(y))
+            ds = torch.where(mv & ineq, (dy - r_s) / Ss_reg, torch.zeros_like(s))
+            delta_w_last = torch.where(moved & (delta_w > 0), delta_w, delta_w_last)
+            # too few negative eigenvalues or a vanishing pivot: the constraint Jacobian is (numerically) rank
+            # deficient -> perturb the constraint block first and retry with the same delta_w
+            degenerate = bad & (singular | (st[:, 1] < m)) & (delta_c == 0)
+            esc = bad & ~degenerate
+            start = torch.where(delta_w_last == 0, torch.full_like(delta_w, o.delta_w_first),
+                                torch.clamp(o.kappa_w_minus * delta_w_last, min=o.delta_w_min))
+            grow = torch.where(delta_w_last == 0, o.kappa_w_plus_first * delta_w, o.kappa_w_plus * delta_w)
+            delta_w_next = torch.where(esc, torch.where(first_try, start, grow), delta_w)
+            delta_c_next = torch.where(degenerate, o.delta_c_bar * mu ** o.kappa_c, delta_c)
+            attempts = torch.where(bad, attempts + 1, torch.zeros_like(attempts))
+            status[bad & ((delta_w_next > o.delta_w_max) | (attempts > 60))] = 3
+            # instances that step start their next iteration from delta_w = delta_c = 0 again
+            delta_w = torch.where(bad, delta_w_next, torch.zeros_like(delta_w))
+            delta_c = torch.where(bad, delta_c_next, torch.zeros_like(delta_c))
+            first_try = torch.where(bad, first_try & ~esc, torch.ones_like(first_try))
+            stalled = bad & (status == -1)
 
             dzL = (mu_c * iL - zL - zL * iL * dx) * fL
             dzU = (mu_c * iU - zU + zU * iU * dx) * fU
@@ -364,7 +370,7 @@ class InteriorPoint:
             phi = barrier(ev['f'], x, s, mu)
             dphi = (gphi_x * dx).sum(1) + (gphi_s * ds).sum(1)
             alpha = a_pr.clone()
-            searching = active.clone()
+            searching = moved & (status == -1)
             accepted_alpha = torch.zeros_like(alpha)
             augment = torch.zeros(B, dtype=torch.bool, device=dev)
             switch_base = (dphi < 0) & (theta <= theta_min)
@@ -398,7 +404,7 @@ class InteriorPoint:
                 accepted_alpha = torch.where(failed, last_alpha, accepted_alpha)
                 augment = augment & ~failed
                 status[failed & (ls_fail >= 3)] = 3
-            ls_fail = torch.where(active & ~failed, torch.zeros_like(ls_fail), ls_fail)
+            ls_fail = torch.where(moved & ~failed, torch.zeros_like(ls_fail), ls_fail)
 
             # ---- filter augmentation, step, multiplier reset ----------------------------------------------
             if bool(augment.any()):
@@ -411,7 +417,7 @@ class InteriorPoint:
             x = x + a * dx
             s = torch.where(ineq, s + a * ds, ceq)
             y = y + a * dy
-            ad = (a_du * active)[:, None]
+            ad = (a_du * moved)[:, None]
             zL, zU, vL, vU = zL + ad * dzL, zU + ad * dzU, vL + ad * dvL, vU + ad * dvU
             dL, dU, eL, eU = slacks(x, s)
 
@@ -421,16 +427,16 @@ class InteriorPoint:
                 return torch.where(f_ > 0, torch.maximum(torch.minimum(z_, hi), lo), z_)
 
             zL, zU, vL, vU = reset(zL, dL, fL), reset(zU, dU, fU), reset(vL, eL, sfL), reset(vU, eU, sfU)
-            iters = iters + active.long()
+            iters = iters + moved.long()
             it += 1
             status[(status == -1) & (iters >= o.max_iter)] = 2
             active = status == -1
             if o.verbose:
                 print(f'      alpha_pr={float(accepted_alpha[0]):.3e} a_max={float(a_pr[0]):.3e} alpha_du={float(a_du[0]):.3e} '
                       f'ls={ls + 1} failed={bool(failed[0])} theta={float(theta[0]):.3e} dphi={float(dphi[0]):.3e} '
-                      f'|dx|={float(dx[0].abs().max()):.2e} |dy|={float(dy[0].abs().max()):.2e} attempts={attempt + 1}')
-            if bool(active.any()):
-                ev = evaluate(x, y, True, active)
+                      f'|dx|={float(dx[0].abs().max()):.2e} |dy|={float(dy[0].abs().max()):.2e} stalled={bool(stalled[0])}')
+            if bool((active & moved).any()):
+                ev = evaluate(x, y, True, active & moved)
 
         status[status < 0] = 2
         E0 = errors(ev, x, s, y, zL, zU, vL, vU, torch.zeros_like(mu))[0]
@@ -438,6 +444,7 @@ class InteriorPoint:
         res.lam_x = zU - zL
         res.status, res.success, res.iterations, res.kkt_error = status, status <= 1, iters, E0
         res.n_iter = it
+        res.factorisations_each = n_fact.cpu().numpy()
         res.t_total = time.perf_counter() - t_start
         return res
 
@@ -485,8 +492,10 @@ class CudaBackend:
             xc, lc = x[idx].contiguous(), (lam_g[idx].contiguous() if derivs else None)
             out = {k: torch.empty((Bc,) + shapes[k][1:], **f64) for k in names}
         lf = None if not derivs else (lam_f if idx is None else lam_f[idx].contiguous())
-        self._scratch = self.F.eval_device(xc, lc, lf, self._vp_rows(idx), None, out['f'], out.get('grad_f'), out['g'],
-                                           out.get('jac'), out.get('hess'), None)
+        if xc.shape[0] > 0:
+            self._scratch = self.F.eval_device(xc, lc, lf, self._vp_rows(idx), None, out['f'], out.get('grad_f'),
+                                               out['g'],
+                                               out.get('jac'), out.get('hess'), None)
         if idx is not None:
             for k in names:
                 full[k].index_copy_(0, idx, out[k])
