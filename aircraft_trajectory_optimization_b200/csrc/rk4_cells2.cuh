@@ -206,6 +206,13 @@ rk4_dir_kernel(const RbDev d, const RbBatch b, const double* __restrict__ scr) {
 #pragma unroll
   for (int i = 0; i < NX; ++i) e[i] = (i == col) ? 1.0 : 0.0;
 
+  // slot indices of this thread's Jacobian column: issued now, consumed after the forward sweep
+  int jsl[NZ];
+  {
+    const int32_t* __restrict__ js0 = d.cell_jslot + (size_t)n * d.cell_nj;
+#pragma unroll
+    for (int c = 0; c < NZ; ++c) jsl[c] = b.jac ? js0[c * NV + col] : -1;
+  }
   // ---------------------------------------------------------------- forward sweep: dk_i = J_i dX_i
   // dX_i = e + a_i (h dk_{i-1} + dh k_{i-1}),  a = (0, 1/2, 1/2, 1);  dk_1..dk_3 are kept in this thread's
   // shared-memory slots for the reverse sweep
@@ -301,7 +308,7 @@ rk4_dir_kernel(const RbDev d, const RbBatch b, const double* __restrict__ scr) {
     if (jac) {
 #pragma unroll
       for (int c = 0; c < NZ; ++c) {
-        const int s = js[c * NV + col];
+        const int s = jsl[c];
         if (s >= 0) jac[s] = d.cell_coef[cr + c] * dout[c];
       }
     }
@@ -378,6 +385,12 @@ rk4_dir_kernel(const RbDev d, const RbBatch b, const double* __restrict__ scr) {
 
   if (!want_h) return;
 
+  // slot indices of this thread's Hessian column: issued before the reverse sweep, consumed after it
+  const int32_t* __restrict__ hs = d.cell_hslot + (size_t)n * d.cell_nh;
+  int hsl[NX + 1];
+#pragma unroll
+  for (int r = 0; r < NX; ++r) hsl[r] = (r <= col) ? hs[r * NL + col] : -1;
+  hsl[NX] = (col == NX) ? hs[NX * NL + NX] : -1;
   // ---------------------------------------------------------------- reverse sweep: dxb_i = W_i dX_i + J_i' dkb_i
   // kb_i = (b_i h / 6) muz + a_{i+1} h xb_{i+1};  dkb_i is its tangent;  hbar gathers a_i (dxb_i . k_{i-1} + xb_i . dk_{i-1})
   double dkb[NZ], dxb[NX];
@@ -428,7 +441,6 @@ rk4_dir_kernel(const RbDev d, const RbBatch b, const double* __restrict__ scr) {
 
   // ---------------------------------------------------------------- hess_l column `col`
   double* __restrict__ H = b.hess + (size_t)p * d.nnzh;
-  const int32_t* __restrict__ hs = d.cell_hslot + (size_t)n * d.cell_nh;
   // objective and input-row bilinear terms that land in this column
   if (col >= NZ && col < NX) {
     const int j = col - NZ;
@@ -441,22 +453,15 @@ rk4_dir_kernel(const RbDev d, const RbBatch b, const double* __restrict__ scr) {
   // pairs (r, col) with r <= col in local order (z, u, h)
 #pragma unroll
   for (int r = 0; r < NZ; ++r) {
-    if (r <= col) {
-      const int s = hs[r * NL + col];
-      if (s >= 0) H[s] = gz[r];
-    }
+    const int s = hsl[r];
+    if (s >= 0) H[s] = gz[r];
   }
 #pragma unroll
   for (int j = 0; j < NU; ++j) {
-    if (NZ + j <= col) {
-      const int s = hs[(NZ + j) * NL + col];
-      if (s >= 0) H[s] = gu[j];
-    }
+    const int s = hsl[NZ + j];
+    if (s >= 0) H[s] = gu[j];
   }
-  if (col == NX) {
-    const int s = hs[NX * NL + NX];
-    if (s >= 0) H[s] = dhb;
-  }
+  if (hsl[NX] >= 0) H[hsl[NX]] = dhb;
   // du entries are owned by the matching u thread: (du_j, du_j) and (h, du_j)
   if (col >= NZ && col < NX) {
     const int j = col - NZ;
