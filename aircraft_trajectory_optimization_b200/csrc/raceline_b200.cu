@@ -85,7 +85,30 @@ cudaError_t launch_cells_t(const RbDev& d, const RbBatch& b, cudaStream_t st) {
       if (e != cudaSuccess) return e;
       configured_dir = true;
     }
-    for (int p0 = 0; p0 < b.B; p0 += RB_RK4_CHUNK) {
+    // Chunks alternate between two side streams and the two halves of the scratch, so that the point kernel of
+    // chunk i+1 (bound by its scratch writes) overlaps the direction kernel of chunk i (bound by arithmetic).
+    static thread_local cudaStream_t side[2] = {nullptr, nullptr};
+    static thread_local cudaEvent_t ev_in = nullptr, ev_out[2] = {nullptr, nullptr};
+    if (!side[0]) {
+      for (int i = 0; i < 2; ++i) {
+        cudaError_t e = cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking);
+        if (e != cudaSuccess) return e;
+        e = cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+      }
+      cudaError_t e = cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming);
+      if (e != cudaSuccess) return e;
+    }
+    const int nchunk = (b.B + RB_RK4_CHUNK - 1) / RB_RK4_CHUNK;
+    const bool fork = nchunk > 1;
+    const size_t half = Rk4Scratch<PF>::doubles((long long)RB_RK4_CHUNK * d.N);
+    if (fork) {
+      cudaEventRecord(ev_in, st);
+      cudaStreamWaitEvent(side[0], ev_in, 0);
+      cudaStreamWaitEvent(side[1], ev_in, 0);
+    }
+    int ci = 0;
+    for (int p0 = 0; p0 < b.B; p0 += RB_RK4_CHUNK, ++ci) {
       RbBatch c = b;
       c.B = b.B - p0 < RB_RK4_CHUNK ? b.B - p0 : RB_RK4_CHUNK;
       c.x += (size_t)p0 * d.nw;
@@ -99,9 +122,17 @@ cudaError_t launch_cells_t(const RbDev& d, const RbBatch& b, cudaStream_t st) {
       if (c.hess) c.hess += (size_t)p0 * d.nnzh;
       if (c.fpart) c.fpart += (size_t)p0 * d.N;
       const long long cc = (long long)c.B * d.N;
-      rk4_point_kernel<PF><<<(unsigned)((cc + 127) / 128), 128, 0, st>>>(d, c, b.cell_scr);
-      rk4_dir_kernel<PF><<<(unsigned)((cc + CPB - 1) / CPB), RB_CELL_THREADS, dir_smem, st>>>(d, c, b.cell_scr);
+      cudaStream_t cs = fork ? side[ci & 1] : st;
+      double* scr = b.cell_scr + (fork ? (size_t)(ci & 1) * half : 0);
+      rk4_point_kernel<PF><<<(unsigned)((cc + 127) / 128), 128, 0, cs>>>(d, c, scr);
+      rk4_dir_kernel<PF><<<(unsigned)((cc + CPB - 1) / CPB), RB_CELL_THREADS, dir_smem, cs>>>(d, c, scr);
       g_launches += 2;
+    }
+    if (fork) {
+      for (int i = 0; i < 2; ++i) {
+        cudaEventRecord(ev_out[i], side[i]);
+        cudaStreamWaitEvent(st, ev_out[i], 0);
+      }
     }
     return cudaGetLastError();
   } else {
@@ -343,7 +374,8 @@ size_t rb_eval_scratch_bytes(const rb_problem* p, int B) {
   if (p->d.transcription == RB_RK4) {
     const long long cells = (long long)(B < RB_RK4_CHUNK ? B : RB_RK4_CHUNK) * p->d.N;
     const int cpb = kVariants[p->variant].rk4_cpb;
-    n += (size_t)((cells + cpb - 1) / cpb) * kVariants[p->variant].rk4_ns * cpb * sizeof(double);
+    // two halves: consecutive chunks run on two streams
+    n += 2 * (size_t)((cells + cpb - 1) / cpb) * kVariants[p->variant].rk4_ns * cpb * sizeof(double);
   }
   return n;
 }
