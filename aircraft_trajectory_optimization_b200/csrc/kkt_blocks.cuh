@@ -445,13 +445,44 @@ kkt_factor_solve_kernel(const RbKktDev d, const RbKktBatch bt) {
       s.rcarry[a * nrhs + r] = s.Zs[cr[a] * nrhs + r];
     }
     __syncthreads();
-    for (int i = warp; i < b; i += nwarps) {
-      const double* __restrict__ yl = YL_g + ((size_t)n * bmax + i) * mmax;
-      for (int r = lane; r < nrhs; r += 32) {
-        double acc = X_g[((size_t)n * bmax + i) * nrhs + r];
-        for (int a = 0; a < m; ++a) acc -= yl[a] * s.rcarry[a * nrhs + r];
-        s.Zs[i * nrhs + r] = acc;
-        X_g[((size_t)n * bmax + i) * nrhs + r] = acc;
+    // x_n = z_n - YL_n x_{n+1}[cr]: 2 x 4 output tiles per thread, YL_n rows read once per tile
+    {
+      const int nct = (nrhs + 3) >> 2, nrt = (b + 1) >> 1;
+      for (int tile = tid; tile < nrt * nct; tile += blockDim.x) {
+        const int tr_ = tile / nct, tc_ = tile - tr_ * nct;
+        const int i0 = tr_ * 2, i1 = (i0 + 1 < b) ? i0 + 1 : i0;
+        int rc[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) rc[c] = (tc_ + c * nct < nrhs) ? tc_ + c * nct : tc_;
+        const double* __restrict__ y0 = YL_g + ((size_t)n * bmax + i0) * mmax;
+        const double* __restrict__ y1 = YL_g + ((size_t)n * bmax + i1) * mmax;
+        double acc[2][4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          acc[0][c] = X_g[((size_t)n * bmax + i0) * nrhs + rc[c]];
+          acc[1][c] = X_g[((size_t)n * bmax + i1) * nrhs + rc[c]];
+        }
+        for (int a = 0; a < m; ++a) {
+          const double l0 = y0[a], l1 = y1[a];
+          const double* __restrict__ xr = s.rcarry + a * nrhs;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const double xv = xr[rc[c]];
+            acc[0][c] -= l0 * xv;
+            acc[1][c] -= l1 * xv;
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (tc_ + c * nct < nrhs) {
+            s.Zs[i0 * nrhs + rc[c]] = acc[0][c];
+            X_g[((size_t)n * bmax + i0) * nrhs + rc[c]] = acc[0][c];
+            if (i0 + 1 < b) {
+              s.Zs[i1 * nrhs + rc[c]] = acc[1][c];
+              X_g[((size_t)n * bmax + i1) * nrhs + rc[c]] = acc[1][c];
+            }
+          }
+        }
       }
     }
     __syncthreads();

@@ -459,6 +459,7 @@ class CudaBackend:
         self.ng = self.st.ng
         self.vp = vp                                   # device tensor (nvp,) or (B, nvp)
         self.K = kkt_solver or KktSolver(self.st)
+        self.refine_tol = 1e-10
         self._buf = {}
 
     def _out(self, name, shape, dev):
@@ -514,8 +515,12 @@ class CudaBackend:
         dx_diag, neg_d, rhs = dx_diag.contiguous(), neg_d.contiguous(), rhs.contiguous()
         sol, status = self.K.factor_solve(hess, jac, dx_diag, neg_d, rhs)
         sol = sol.clone()
+        scale = torch.clamp(rhs.abs().amax(1), min=1.0)
         for _ in range(refine_steps):
             r = rhs - self.K.matvec(hess, jac, dx_diag, neg_d, sol)
+            # iterative refinement only while some instance is above the fp64 noise floor of its right-hand side
+            if not bool(((r.abs().amax(1) / scale) > self.refine_tol).any()):
+                break
             sol = sol + self.K.resolve(hess, jac, dx_diag, neg_d, r)
         if idx is None:
             return sol, status
