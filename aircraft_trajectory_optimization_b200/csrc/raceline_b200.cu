@@ -24,6 +24,7 @@
 #include "colloc_cells.cuh"
 #include "simple_rows.cuh"
 #include "kkt_blocks.cuh"
+#include "kkt_big.cuh"
 
 namespace {
 

@@ -20,7 +20,7 @@ from oracle.cpu_backend import OracleBackend                                    
 from aircraft_trajectory_optimization_b200.ipm import InteriorPoint, IpmOptions  # noqa: E402
 from aircraft_trajectory_optimization_b200.kkt import build_kkt_structure        # noqa: E402
 
-CASES = [('race_param_rk4_point', 7), ('race_global_rk4_point', 7)]
+CASES = [('race_param_rk4_point', 7), ('race_global_rk4_point', 7), ('fig8_global_colloc_point', 8)]
 
 
 def solve_cpu(name, N, max_iter=400):

@@ -17,11 +17,11 @@ LAP_RTOL = 1e-6
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('name', ['race_param_rk4_point', 'race_global_rk4_point'])
-def test_point_mass_solve_matches_cpu_golden(name, built_library):
+@pytest.mark.parametrize('name,N', [('race_param_rk4_point', 7), ('race_global_rk4_point', 7),
+                                    ('fig8_global_colloc_point', 8)])
+def test_point_mass_solve_matches_cpu_golden(name, N, built_library):
     from oracle.nlp_functions import OracleNLP
     from test_ipm_cpu import _kkt_conditions
-    N = 7
     prod, ref = build_case(name, N=N)
     st = prod.structure
     res = prod.solve()
@@ -31,7 +31,7 @@ def test_point_mass_solve_matches_cpu_golden(name, built_library):
     assert abs(res.time - float(gold['lap'])) <= LAP_RTOL * float(gold['lap'])
     assert np.abs(prod.sol['x'] - gold['x']).max() <= 1e-5
     _kkt_conditions(st, OracleNLP(ref, build_hess=False), prod.sol['x'], prod.sol['lam_g'], prod.sol['lam_x'])
-    assert res.feasible and len(res.states) == st.N and abs(sum(res.step_sizes) - res.time) < 1e-12
+    assert res.feasible and len(res.states) == st.N * (st.K + 1) and abs(sum(res.step_sizes) - res.time) < 1e-12
 
 
 @pytest.mark.gpu

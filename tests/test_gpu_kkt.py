@@ -9,6 +9,8 @@ import pytest
 from cases import CASES, build_case, build_product, eval_point
 
 RK4_CASES = [c for c, v in CASES.items() if v[3]]
+# collocation structures go through the large-block kernel (csrc/kkt_big.cuh)
+KKT_CASES = RK4_CASES + ['fig8_global_colloc_point', 'fig8_global_colloc_drone', 'obs_param_colloc_point']
 
 
 def _inputs(st, F, B, seed=0):
@@ -23,7 +25,7 @@ def _inputs(st, F, B, seed=0):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('name', RK4_CASES)
+@pytest.mark.parametrize('name', KKT_CASES)
 def test_kkt_solve_matches_sparse_lu(name, built_library):
     import torch
     from oracle.kkt_blocks_ref import sparse_solve, kkt_matrix

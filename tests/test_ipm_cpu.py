@@ -58,7 +58,7 @@ def test_point_mass_solve_matches_golden():
 def test_golden_solutions_are_kkt_points():
     ''' the committed golden solutions satisfy the optimality conditions of the oracle's NLP '''
     from oracle.nlp_functions import OracleNLP
-    for name, N in (('race_param_rk4_point', 7), ('race_global_rk4_point', 7)):
+    for name, N in (('race_param_rk4_point', 7), ('race_global_rk4_point', 7), ('fig8_global_colloc_point', 8)):
         prod, ref = build_case(name, N=N)
         gold = np.load(os.path.join(GOLD, f'ipm_{name}_N{N}.npz'))
         _kkt_conditions(prod.structure, OracleNLP(ref, build_hess=False), gold['x'], gold['lam_g'], gold['lam_x'])
