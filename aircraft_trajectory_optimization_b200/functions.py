@@ -48,7 +48,9 @@ class _Desc(ctypes.Structure):
 EXPORTS = ['rb_last_error', 'rb_device_count', 'rb_set_device', 'rb_problem_create', 'rb_problem_destroy',
            'rb_problem_nvp', 'rb_sparsity_size', 'rb_sparsity_get', 'rb_eval_scratch_bytes', 'rb_eval_batch',
            'rb_nlp_f', 'rb_nlp_g', 'rb_nlp_grad_f', 'rb_nlp_jac_g', 'rb_nlp_hess_l', 'rb_nlp_eval_all',
-           'rb_launch_count', 'rb_profile_enable', 'rb_profile_cell_ms', 'rb_fp64_peak']
+           'rb_launch_count', 'rb_profile_enable', 'rb_profile_cell_ms', 'rb_fp64_peak',
+           'rb_kkt_create', 'rb_kkt_destroy', 'rb_kkt_factor_bytes', 'rb_kkt_factor_solve', 'rb_kkt_resolve',
+           'rb_kkt_matvec']
 
 
 def load_library():
