@@ -1,4 +1,5 @@
-// Collocation interval-cell kernel: one warp per (problem, interval), K = 7 Legendre points.
+// Collocation interval-cell kernel: one warp per (problem, interval), K = 7 Legendre points; the generated point
+// functions of the RB_COLLOC_WPB intervals of a CTA run side by side on consecutive threads.
 //
 // Reference definition of what is computed: drone3d/raceline/base_raceline.py:398-434 (ode rows:
 // [sdot >= 0], defect f - sum_j C[j][k] Z_j / H, dU - sum_j C[j][k] U_j / H), :460-490 / :1132-1181
@@ -63,8 +64,10 @@ colloc_cells_kernel(const RbDev d, const RbBatch b) {
   constexpr int NZ = L::NZ, NU = L::NU, NX = L::NX, S = L::S, NJ = L::NJ, NW = L::NW, KP = RB_KP;
   extern __shared__ double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long cell = (long long)blockIdx.x * RB_COLLOC_WPB + warp;
-  if (cell >= (long long)b.B * d.N) return;
+  const long long ncell = (long long)b.B * d.N;
+  const long long cell_raw = (long long)blockIdx.x * RB_COLLOC_WPB + warp;
+  const bool valid = cell_raw < ncell;                     // the last CTA may be short of cells: its spare warps
+  const long long cell = valid ? cell_raw : ncell - 1;     // recompute the last cell and store nothing
   const int p = (int)(cell / d.N);
   const int n = (int)(cell - (long long)p * d.N);
   const int nju = d.cell_nj, nhu = d.cell_nh;
@@ -85,8 +88,8 @@ colloc_cells_kernel(const RbDev d, const RbBatch b) {
   const int32_t* __restrict__ tj = d.tmpl_j;
   const int32_t* __restrict__ th = d.tmpl_h;
   const double sig = b.lam_f ? b.lam_f[p] : 1.0;
-  const bool want_h = b.hess != nullptr;
-  const bool want_j = b.jac != nullptr;
+  const bool want_h = valid && b.hess != nullptr;
+  const bool want_j = valid && b.jac != nullptr;
 
   // ---- stage variables, multipliers; clear the images -------------------------------------------
   const size_t wbase = (size_t)d.N + (size_t)n * KP * S;
@@ -105,33 +108,35 @@ colloc_cells_kernel(const RbDev d, const RbBatch b) {
   const double h = xs[0];
   const double hi = 1.0 / h, hi2 = hi * hi, hi3 = hi2 * hi;
 
-  // ---- phase A: generated point functions, one collocation point per lane ------------------------
-  if (lane >= 1 && lane < KP) {
-    const int k = lane;
-    double x[NX], kb[NZ], fc[PF::NFC], vp[PF::NVP], f[NZ];
+  // ---- phase A: generated point functions.  The 7 interior points of the RB_COLLOC_WPB cells of this CTA are
+  // spread over consecutive threads (28 of the 32 lanes of warp 0 busy) instead of 7 lanes in every warp.
+  __syncthreads();                                   // every cell of the CTA has been staged
+  if (threadIdx.x < RB_COLLOC_WPB * 7) {
+    const int cl = threadIdx.x / 7, k = 1 + threadIdx.x - cl * 7;
+    const long long cg_raw = (long long)blockIdx.x * RB_COLLOC_WPB + cl;
+    const long long cg = cg_raw < ncell ? cg_raw : ncell - 1;
+    const int pp = (int)(cg / d.N);
+    const int nn = (int)(cg - (long long)pp * d.N);
+    double* xs_c = smem + (size_t)cl * colloc_cell_doubles<PF>(nju, nhu);
+    double* lam_c = xs_c + L::NXS;
+    double* fv_c = lam_c + L::NCR;
+    double* Jst_c = fv_c + 7 * NZ;
+    double* Hst_c = Jst_c + nju;
+    double x[NX], kb[NZ], f[NZ];
 #pragma unroll
-    for (int i = 0; i < NX; ++i) x[i] = xs[1 + k * S + i];
+    for (int i = 0; i < NX; ++i) x[i] = xs_c[1 + k * S + i];
 #pragma unroll
-    for (int i = 0; i < NZ; ++i) kb[i] = lam_l[L::RF + (k - 1) * NZ + i];
-    if (PF::USES_FC) {
-      const double* __restrict__ fcp =
-          (b.fc_b ? b.fc_b + (size_t)p * d.N * KP * PF::NFC : d.fc) + ((size_t)n * KP + k) * PF::NFC;
+    for (int i = 0; i < NZ; ++i) kb[i] = lam_c[L::RF + (k - 1) * NZ + i];
+    const double* __restrict__ fcp =
+        PF::USES_FC ? (b.fc_b ? b.fc_b + (size_t)pp * d.N * KP * PF::NFC : d.fc) + ((size_t)nn * KP + k) * PF::NFC : d.fc;
+    const double* __restrict__ vpp = b.vp + (size_t)pp * b.vp_stride;
+    PF::fJW_scatter(x, kb, fcp, vpp, f, Jst_c, tj + L::JF + (k - 1) * NJ, Hst_c, th + L::HW + (k - 1) * NW);
 #pragma unroll
-      for (int i = 0; i < PF::NFC; ++i) fc[i] = fcp[i];
-    } else {
-#pragma unroll
-      for (int i = 0; i < PF::NFC; ++i) fc[i] = 0.0;
-    }
-    const double* __restrict__ vpp = b.vp + (size_t)p * b.vp_stride;
-#pragma unroll
-    for (int i = 0; i < PF::NVP; ++i) vp[i] = vpp[i];
-    PF::fJW_scatter(x, kb, fc, vp, f, Jst, tj + L::JF + (k - 1) * NJ, Hst, th + L::HW + (k - 1) * NW);
-#pragma unroll
-    for (int i = 0; i < NZ; ++i) fv[(k - 1) * NZ + i] = f[i];
+    for (int i = 0; i < NZ; ++i) fv_c[(k - 1) * NZ + i] = f[i];
   }
-  __syncwarp();
+  __syncthreads();
 
-  double* __restrict__ g = b.g ? b.g + (size_t)p * d.ng : nullptr;
+  double* __restrict__ g = (valid && b.g) ? b.g + (size_t)p * d.ng : nullptr;
 
   // ---- phase B: transcription terms (lane-strided flat loops over the slot groups) ---------------
   // sdot rows (parametric frame):  P0_k / h
@@ -252,10 +257,10 @@ colloc_cells_kernel(const RbDev d, const RbBatch b) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) fsum += __shfl_xor_sync(0xffffffffu, fsum, o);
     if (lane == 0) {
-      if (b.fpart) b.fpart[(size_t)p * d.N + n] = fsum * h;
-      if (b.grad_f) b.grad_f[(size_t)p * d.nw + n] = fsum;
+      if (valid && b.fpart) b.fpart[(size_t)p * d.N + n] = fsum * h;
+      if (valid && b.grad_f) b.grad_f[(size_t)p * d.nw + n] = fsum;
     }
-    if (b.grad_f) {
+    if (valid && b.grad_f) {
       double* __restrict__ gf = b.grad_f + (size_t)p * d.nw + wbase;
       for (int i = lane; i < KP * S; i += 32) {
         const int k = i / S, c = i - k * S;

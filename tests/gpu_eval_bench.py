@@ -9,7 +9,8 @@ import bench
 from aircraft_trajectory_optimization_b200.functions import NlpFunctions, load_library
 from aircraft_trajectory_optimization_b200.models import vehicle_params
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-prod = build_product(bench.CASE)
+case = sys.argv[2] if len(sys.argv) > 2 else bench.CASE
+prod = build_product(case)
 st = prod.structure
 F = NlpFunctions(st, prod.vehicle_config, device=0)
 X, L, VP = bench.make_inputs(st, vehicle_params(prod.vehicle_config), B, 0)
@@ -26,4 +27,5 @@ e0.record()
 for _ in range(5): step()
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 5
-print(os.environ.get('RACELINE_B200_LIB', 'default'), f'B={B} {ms:.2f} ms/step {B / ms * 1e3:.0f} evals/s checksum {float(h.sum()):.6e}')
+ab = bench.algorithmic_bytes(st)
+print(os.environ.get('RACELINE_B200_LIB', 'default'), case, f'B={B} {ms:.2f} ms/step {B / ms * 1e3:.0f} evals/s; {ab} B/eval -> {ab * B / ms / 1e6:.0f} GB/s algorithmic; checksum {float(h.sum()):.6e}')
