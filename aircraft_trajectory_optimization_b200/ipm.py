@@ -56,6 +56,7 @@ class IpmOptions:
     s_phi: float = 2.3
     eta_phi: float = 1e-8
     max_ls: int = 30
+    ls_width: int = 4                  # step lengths tried per evaluation call in the line search
     filter_size: int = 64
     delta_w_first: float = 1e-4
     delta_w_min: float = 1e-20
@@ -375,27 +376,59 @@ class InteriorPoint:
             augment = torch.zeros(B, dtype=torch.bool, device=dev)
             switch_base = (dphi < 0) & (theta <= theta_min)
             last_alpha = alpha.clone()
-            for ls in range(o.max_ls):
-                xt = x + alpha[:, None] * dx
-                st_ = torch.where(ineq, s + alpha[:, None] * ds, ceq)
-                evt = evaluate(xt, y, False, searching)
-                th_t = infeas(evt['g'], st_).abs().sum(1)
-                ph_t = barrier(evt['f'], xt, st_, mu)
-                okfin = torch.isfinite(th_t) & torch.isfinite(ph_t)
-                in_filter = ((th_t[:, None] >= (1 - o.gamma_theta) * filt_theta)
-                             & (ph_t[:, None] >= filt_phi - o.gamma_phi * filt_theta)).any(1)
-                sw = switch_base & (alpha * (-dphi).clamp(min=0) ** o.s_phi > o.delta_ls * theta ** o.s_theta)
-                armijo = ph_t <= phi + o.eta_phi * alpha * dphi
-                suff = (th_t <= (1 - o.gamma_theta) * theta) | (ph_t <= phi - o.gamma_phi * theta)
-                ok = okfin & ~in_filter & (th_t <= theta_max) & torch.where(sw, armijo, suff)
-                acc_now = searching & ok
-                accepted_alpha = torch.where(acc_now, alpha, accepted_alpha)
-                augment = torch.where(acc_now, ~(sw & armijo), augment)
-                searching = searching & ~ok
-                last_alpha = torch.where(searching, alpha, last_alpha)
-                if not bool(searching.any()):
+            # Every round tries `ls_width` step lengths alpha, alpha/2, ... of every instance still searching in ONE
+            # evaluation call (an evaluation costs microseconds per instance; a round trip through the driver does
+            # not) and accepts the longest admissible one -- the same step a sequential backtracking search takes.
+            Kw = max(1, int(o.ls_width))
+            halves = 0.5 ** torch.arange(Kw, dtype=dt, device=dev)
+            ls = 0
+            while ls < o.max_ls:
+                rows = torch.nonzero(searching).squeeze(1)
+                if rows.numel() == 0:
                     break
-                alpha = torch.where(searching, 0.5 * alpha, alpha)
+                ns = rows.numel()
+                al = alpha[rows][:, None] * halves[None, :]                                    # [ns, Kw]
+                xt = x[rows][:, None, :] + al[:, :, None] * dx[rows][:, None, :]               # [ns, Kw, n]
+                st_ = torch.where(ineq[rows][:, None, :], s[rows][:, None, :] + al[:, :, None] * ds[rows][:, None, :],
+                                  ceq[rows][:, None, :])
+                t0 = time.perf_counter()
+                evt = be.eval_points(xt.reshape(ns * Kw, n), rows.repeat_interleave(Kw))
+                if dev.type == 'cuda':
+                    torch.cuda.synchronize(dev)
+                res.t_eval += time.perf_counter() - t0
+                res.n_eval += 1
+                g_t, f_t = evt['g'].reshape(ns, Kw, m), evt['f'].reshape(ns, Kw)
+                th_t = torch.where(eq[rows][:, None, :], g_t - ceq[rows][:, None, :], g_t - st_).abs().sum(2)
+                # barrier function at the trial points
+                lg = lambda d_, f_: (torch.log(torch.where(f_ > 0, d_, torch.ones_like(d_))) * f_).sum(2)
+                r_ = lambda t: t[rows][:, None, :]
+                dLt, dUt, eLt, eUt = xt - r_(xL), r_(xU) - xt, st_ - r_(sL), r_(sU) - st_
+                mu_r = mu[rows][:, None]
+                ph_t = f_t - mu_r * (lg(dLt, r_(fL)) + lg(dUt, r_(fU)) + lg(eLt, r_(sfL)) + lg(eUt, r_(sfU)))
+                ph_t = ph_t + o.kappa_d * mu_r * ((dLt * r_(dampL)).sum(2) + (dUt * r_(dampU)).sum(2)
+                                                  + (eLt * r_(sdampL)).sum(2) + (eUt * r_(sdampU)).sum(2))
+                okfin = torch.isfinite(th_t) & torch.isfinite(ph_t)
+                ft, fp = filt_theta[rows][:, None, :], filt_phi[rows][:, None, :]
+                in_filter = ((th_t[:, :, None] >= (1 - o.gamma_theta) * ft)
+                             & (ph_t[:, :, None] >= fp - o.gamma_phi * ft)).any(2)
+                th0, ph0, dph = theta[rows][:, None], phi[rows][:, None], dphi[rows][:, None]
+                sw = switch_base[rows][:, None] & (al * (-dph).clamp(min=0) ** o.s_phi > o.delta_ls * th0 ** o.s_theta)
+                armijo = ph_t <= ph0 + o.eta_phi * al * dph
+                suff = (th_t <= (1 - o.gamma_theta) * th0) | (ph_t <= ph0 - o.gamma_phi * th0)
+                ok = okfin & ~in_filter & (th_t <= theta_max[rows][:, None]) & torch.where(sw, armijo, suff)
+                # never accept a candidate beyond the max_ls-th halving
+                ok = ok & ((ls + torch.arange(Kw, device=dev)) < o.max_ls)[None, :]
+                any_ok = ok.any(1)
+                first = torch.argmax(ok.to(torch.int8), dim=1)                                   # first admissible halving
+                pick = first[:, None]
+                acc_rows = rows[any_ok]
+                accepted_alpha[acc_rows] = al.gather(1, pick).squeeze(1)[any_ok]
+                augment[acc_rows] = ~(sw & armijo).gather(1, pick).squeeze(1)[any_ok]
+                searching[acc_rows] = False
+                rej_rows = rows[~any_ok]
+                last_alpha[rej_rows] = al[~any_ok, Kw - 1]
+                alpha[rej_rows] = al[~any_ok, Kw - 1] * 0.5
+                ls += Kw
             # failed searches: reset the filter and take the shortest trial step
             failed = searching
             if bool(failed.any()):
@@ -433,7 +466,7 @@ class InteriorPoint:
             active = status == -1
             if o.verbose:
                 print(f'      alpha_pr={float(accepted_alpha[0]):.3e} a_max={float(a_pr[0]):.3e} alpha_du={float(a_du[0]):.3e} '
-                      f'ls={ls + 1} failed={bool(failed[0])} theta={float(theta[0]):.3e} dphi={float(dphi[0]):.3e} '
+                      f'ls<={ls} failed={bool(failed[0])} theta={float(theta[0]):.3e} dphi={float(dphi[0]):.3e} '
                       f'|dx|={float(dx[0].abs().max()):.2e} |dy|={float(dy[0].abs().max()):.2e} stalled={bool(stalled[0])}')
             if bool((active & moved).any()):
                 ev = evaluate(x, y, True, active & moved)
@@ -504,6 +537,16 @@ class CudaBackend:
             # the driver keeps these until the next derivative evaluation: hand out the persistent buffers
             return dict(full)
         return {k: v.clone() for k, v in full.items()}
+
+    def eval_points(self, x_rows, inst):
+        """ f and g at arbitrary trial points; inst[r] = instance (vehicle parameters) of row r """
+        st, dev, R = self.st, x_rows.device, x_rows.shape[0]
+        f = torch.empty(R, dtype=torch.float64, device=dev)
+        g = torch.empty(R, st.ng, dtype=torch.float64, device=dev)
+        vp = self.vp if self.vp.dim() == 1 else self.vp[inst].contiguous()
+        if R > 0:
+            self.F.eval_device(x_rows.contiguous(), None, None, vp, None, f, None, g, None, None, None)
+        return dict(f=f, g=g)
 
     def kkt_matvec(self, hess, jac, dx_diag, neg_d, vec):
         return self.K.matvec(hess, jac, dx_diag.contiguous(), neg_d.contiguous(), vec.contiguous())

@@ -133,10 +133,17 @@ def build_kkt_structure(st) -> KKTStructure:
     # Triple n = [c_{n-1}, x_n; rows that are the identity on x_n].  The loop closes through triple 0 =
     # triple N = [c_{N-1}, x_0; closure rows], which becomes the border: x_0 is `low` (it couples to
     # triple 1 like any x_{n-1} does), c_{N-1} is `high` (anything touching it is a border row).
+    # Collocation (K > 0): c_{N-1} holds the interior points of the last interval (~150 variables); it stays in
+    # the chain as a block of its own, [c_{N-1}; defect / rate rows of the last interval], and only the closure
+    # rows (which are the identity on x_0) join x_0 in the border -- otherwise the border would be as large as a
+    # stage block.  Shooting (K = 0): c_{N-1} is five variables and goes to the border with its rows.
+    chain_last = st.K > 0
     LOW, HIGH = -1, N
+    top = N if chain_last else N - 1                 # triple index of the first chain block
     tt = t.copy()
     tt[(t == 0)] = LOW
-    tt[(t == N)] = HIGH
+    if not chain_last:
+        tt[(t == N)] = HIGH
     # far couplings that are not part of the loop (the equal-step star rows of the global frame): the
     # variable at the low end of several far rows moves to the border as a `low` variable
     for _ in range(8):
@@ -154,14 +161,22 @@ def build_kkt_structure(st) -> KKTStructure:
     rmax = np.full(ng, LOW, dtype=np.int64)
     np.maximum.at(rmax, jr, tt[jc])
     row_t = np.where(rmax == LOW, HIGH, rmax)
+    if chain_last:
+        # rows of the last block that reach back to x_0 are the closure rows: border
+        touches_low = np.zeros(ng, dtype=bool)
+        touches_low[jr[tt[jc] == LOW]] = True
+        row_t = np.where((row_t == N) & touches_low, HIGH + 1, row_t)
+        BORDER_T = HIGH + 1
+    else:
+        BORDER_T = HIGH
 
-    # chain blocks are the triples N-1, N-2, ..., 1 in that order (the sweep runs backward in time: a
-    # Riccati recursion); block index Nc = N - 1 is the border
-    Nc = N - 1
-    to_chain = lambda tv: np.where((tv == LOW) | (tv == HIGH), Nc, Nc - tv)
+    # chain blocks are the triples top, top-1, ..., 1 in that order (the sweep runs backward in time: a
+    # Riccati recursion); block index Nc is the border
+    Nc = top
+    to_chain = lambda tv: np.where((tv == LOW) | (tv == BORDER_T), Nc, Nc - tv)
     blk = np.empty(nw + ng, dtype=np.int64)
     blk[:nw] = to_chain(tt)
-    blk[nw:] = to_chain(row_t)
+    blk[nw:] = to_chain(np.where(rmax == LOW, BORDER_T, row_t))
     N = Nc
 
     # ---- structural rank of the equality rows inside every triple -------------------------------------

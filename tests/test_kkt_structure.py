@@ -25,7 +25,7 @@ def _kkt_inputs(st, nlp, seed):
     return hess, jac, dxd, D, rhs
 
 
-@pytest.mark.parametrize('name', RK4_CASES)
+@pytest.mark.parametrize('name', RK4_CASES + ['fig8_global_colloc_point', 'fig8_param_colloc_point'])
 def test_block_tables_reproduce_the_sparse_solve(name):
     from oracle.nlp_functions import OracleNLP
     from oracle.kkt_blocks_ref import kkt_matrix, sparse_solve, block_solve
@@ -36,7 +36,7 @@ def test_block_tables_reproduce_the_sparse_solve(name):
     # every unknown appears exactly once
     assert np.array_equal(np.sort(ks.unk), np.arange(st.nw + st.ng))
     assert ks.blk_ptr[-1] == st.nw + st.ng and ks.nb == ks.blk_ptr[-1] - ks.blk_ptr[-2]
-    for seed in range(2):
+    for seed in range(2 if st.K == 0 else 1):
         hess, jac, dxd, D, rhs = _kkt_inputs(st, nlp, seed)
         K = kkt_matrix(st, hess, jac, dxd, D)
         ref_sol = sparse_solve(st, hess, jac, dxd, D, rhs)
@@ -61,4 +61,4 @@ def test_collocation_structure_builds():
     ''' collocation intervals give much larger triples (interior points belong to c_n) '''
     prod = build_product('fig8_global_colloc_point', small=True)
     ks = build_kkt_structure(prod.structure)
-    assert ks.bmax > 100
+    assert ks.bmax > 100 and ks.nb < 64      # c_{N-1} stays in the chain: the border is x_0 + closure rows
