@@ -60,7 +60,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.gpu_index}', f'--query-gpu={self.Q}',
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '20'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -319,7 +319,9 @@ def main():
     ap.add_argument('--no-solves', action='store_true', help='skip the converged-solves leg')
     ap.add_argument('--solves-batch', type=int, default=1024, help='multi-start instances per GPU in the solves leg')
     ap.add_argument('--solves-window', type=int, default=888, help='instances iterating at a time (continuous batching)')
-    ap.add_argument('--solves-max-iter', type=int, default=500)
+    ap.add_argument('--solves-max-iter', type=int, default=300,
+                    help='iteration cap per instance in the multi-start sweep (p99 of converged instances is ~280; '
+                         'the reference sets 1000 for its single solves)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
@@ -372,12 +374,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()         # samples cover warm-up, the timed region and the end-to-end leg (all under load)
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     lib.rb_profile_enable(1)
     l0 = lib.rb_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -391,7 +393,6 @@ def main():
     cell_ms, cell_n = ctypes.c_double(0), ctypes.c_int(0)
     lib.rb_profile_cell_ms(ctypes.byref(cell_ms), ctypes.byref(cell_n))
     lib.rb_profile_enable(0)
-    clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
@@ -427,6 +428,7 @@ def main():
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_value = world * Be * e2e_steps / float(dt.item())
+    clocks = sampler.stop() if rank == 0 else None
     h2d = 8 * Be * (st.nw + st.ng + F.nvp + 1)
     d2h = 8 * Be * (1 + st.nw + st.ng + st.nnz_jac + st.nnz_hess)
     # spot check: the host path and the device path agree bit for bit on instance 0
@@ -453,8 +455,12 @@ def main():
         nv = st.nz + st.nu + 1
         nj, nwz = len(meta['J']), len(meta['W'])
         flop_eval = st.N * (4 * (meta['ops']['fJ_s'] + meta['ops']['vjpW_s']) + nv * 4 * (2 * nj + 2 * nwz))
+        # DRAM bytes of the two shooting kernels per 128-instance chunk, from the ncu --set full capture of this
+        # command (profiles/r01_ncu_rk4_cells.txt: point 60.9 + 439.6 MB, direction 452.7 + 176.3 MB), scaled to a step
+        traffic_bytes = (60.870144e6 + 439.586560e6 + 452.706048e6 + 176.329984e6) * (B / 128.0)
         roofline = dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
-                        traffic=None, peak_source=peak_src, kernel='rk4_point_kernel + rk4_dir_kernel <PF_drone_quat_param_gr> (all chunks of a step)',
+                        traffic=traffic_bytes, traffic_unit='bytes per step (ncu dram__bytes_read+write, profiles/r01_ncu_rk4_cells.txt)',
+                        algorithmic_bytes_per_step=ab * B, peak_source=peak_src, kernel='rk4_point_kernel + rk4_dir_kernel <PF_drone_quat_param_gr> (all chunks of a step)',
                         algorithmic_bytes_per_eval=ab, evals_per_launch=B, kernel_ms=cell_avg_ms,
                         kernel_share_of_step=cell_ms.value / total_ms,
                         fp64=dict(note='the shooting kernels are FP64 / latency bound, not HBM bound: fp64 arithmetic '
