@@ -357,17 +357,32 @@ colloc_cells_kernel(const RbDev d, const RbBatch b) {
   if (want_j) {
     double* __restrict__ jac = b.jac + (size_t)p * d.nnzj;
     const int32_t* __restrict__ js = d.cell_jslot + (size_t)n * nju;
-    for (int i = lane; i < nju; i += 32) {
-      const int s = js[i];
-      if (s >= 0) jac[s] = Jst[i];
+    // slot indices are fetched eight at a time so that their latency overlaps
+    for (int i0 = 0; i0 < nju; i0 += 256) {
+      int sl[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * 32 + lane;
+        sl[u] = i < nju ? js[i] : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (sl[u] >= 0) jac[sl[u]] = Jst[i0 + u * 32 + lane];
     }
   }
   if (want_h) {
     double* __restrict__ H = b.hess + (size_t)p * d.nnzh;
     const int32_t* __restrict__ hs = d.cell_hslot + (size_t)n * nhu;
-    for (int i = lane; i < nhu; i += 32) {
-      const int s = hs[i];
-      if (s >= 0) H[s] = Hst[i];
+    for (int i0 = 0; i0 < nhu; i0 += 256) {
+      int sl[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * 32 + lane;
+        sl[u] = i < nhu ? hs[i] : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (sl[u] >= 0) H[sl[u]] = Hst[i0 + u * 32 + lane];
     }
   }
 }
