@@ -168,7 +168,9 @@ struct Workspace {
   double *x = nullptr, *lam_g = nullptr, *lam_f = nullptr, *vp = nullptr;
   double *f = nullptr, *grad_f = nullptr, *g = nullptr, *jac = nullptr, *hess = nullptr;
   void* scratch = nullptr;
-  cudaStream_t stream = nullptr;
+  void* scratch2 = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;
+  cudaEvent_t ev_done2 = nullptr;
 };
 
 }  // namespace
@@ -201,16 +203,19 @@ void free_ws(Workspace& w) {
   for (double* q : {w.x, w.lam_g, w.lam_f, w.vp, w.f, w.grad_f, w.g, w.jac, w.hess})
     if (q) cudaFree(q);
   if (w.scratch) cudaFree(w.scratch);
-  w = Workspace{.stream = w.stream};
+  if (w.scratch2) cudaFree(w.scratch2);
+  w = Workspace{.stream = w.stream, .stream2 = w.stream2, .ev_done2 = w.ev_done2};
 }
 
 int ensure_ws(rb_problem* p, int B) {
   Workspace& w = p->ws;
-  if (!w.stream) CK(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+  if (!w.stream) {
+    CK(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&w.stream2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&w.ev_done2, cudaEventDisableTiming));
+  }
   if (w.B >= B) return 0;
-  cudaStream_t st = w.stream;
   free_ws(w);
-  w.stream = st;
   const RbDev& d = p->d;
   auto alloc = [&](double** q, size_t n) -> cudaError_t { return cudaMalloc((void**)q, n * sizeof(double)); };
   CK(alloc(&w.x, (size_t)B * d.nw));
@@ -223,6 +228,7 @@ int ensure_ws(rb_problem* p, int B) {
   CK(alloc(&w.jac, (size_t)B * (d.nnzj > 0 ? d.nnzj : 1)));
   CK(alloc(&w.hess, (size_t)B * (d.nnzh > 0 ? d.nnzh : 1)));
   CK(cudaMalloc(&w.scratch, rb_eval_scratch_bytes(p, B)));
+  CK(cudaMalloc(&w.scratch2, rb_eval_scratch_bytes(p, B)));
   w.B = B;
   return 0;
 }
@@ -344,9 +350,12 @@ int rb_problem_create(const rb_problem_desc* s, rb_problem** out) {
 void rb_problem_destroy(rb_problem* p) {
   if (!p) return;
   for (void* q : p->owned) cudaFree(q);
-  cudaStream_t st = p->ws.stream;
+  cudaStream_t st = p->ws.stream, st2 = p->ws.stream2;
+  cudaEvent_t ev = p->ws.ev_done2;
   free_ws(p->ws);
   if (st) cudaStreamDestroy(st);
+  if (st2) cudaStreamDestroy(st2);
+  if (ev) cudaEventDestroy(ev);
   delete p;
 }
 
@@ -514,29 +523,40 @@ static int host_eval(const rb_problem* cp, int B, const double* x, const double*
   if (ensure_ws(p, B)) return 1;
   Workspace& w = p->ws;
   const RbDev& d = p->d;
-  cudaStream_t st = w.stream;
-  CK(cudaMemcpyAsync(w.x, x, (size_t)B * d.nw * sizeof(double), cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(w.vp, vp, (size_t)B * p->nvp * sizeof(double), cudaMemcpyHostToDevice, st));
-  const double* dl = nullptr;
-  const double* dlf = nullptr;
-  if (hess) {
-    if (!lam_g && d.ng > 0) return fail("nlp_hess_l needs lam_g");
-    if (d.ng > 0) CK(cudaMemcpyAsync(w.lam_g, lam_g, (size_t)B * d.ng * sizeof(double), cudaMemcpyHostToDevice, st));
-    dl = w.lam_g;
-    if (lam_f) {
-      CK(cudaMemcpyAsync(w.lam_f, lam_f, (size_t)B * sizeof(double), cudaMemcpyHostToDevice, st));
-      dlf = w.lam_f;
+  if (hess && !lam_g && d.ng > 0) return fail("nlp_hess_l needs lam_g");
+  // Chunks of instances alternate between two streams: the device->host copies of one chunk (the bulk of the
+  // bytes: jac_g and hess_l values) overlap the host->device copies and kernels of the next one.
+  const int CH = 64;
+  const size_t nw = d.nw, ng = d.ng, nj = d.nnzj, nh = d.nnzh, nvp = p->nvp;
+  int ci = 0;
+  for (int p0 = 0; p0 < B; p0 += CH, ++ci) {
+    const int Bc = B - p0 < CH ? B - p0 : CH;
+    cudaStream_t st = (ci & 1) ? w.stream2 : w.stream;
+    void* scr = (ci & 1) ? w.scratch2 : w.scratch;
+    CK(cudaMemcpyAsync(w.x + p0 * nw, x + p0 * nw, Bc * nw * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(w.vp + p0 * nvp, vp + p0 * nvp, Bc * nvp * sizeof(double), cudaMemcpyHostToDevice, st));
+    const double* dl = nullptr;
+    const double* dlf = nullptr;
+    if (hess) {
+      if (ng > 0) CK(cudaMemcpyAsync(w.lam_g + p0 * ng, lam_g + p0 * ng, Bc * ng * sizeof(double), cudaMemcpyHostToDevice, st));
+      dl = w.lam_g + p0 * ng;
+      if (lam_f) {
+        CK(cudaMemcpyAsync(w.lam_f + p0, lam_f + p0, Bc * sizeof(double), cudaMemcpyHostToDevice, st));
+        dlf = w.lam_f + p0;
+      }
     }
+    if (rb_eval_batch(p, Bc, w.x + p0 * nw, dl, dlf, w.vp + p0 * nvp, p->nvp, nullptr, f ? w.f + p0 : nullptr,
+                      grad_f ? w.grad_f + p0 * nw : nullptr, g ? w.g + p0 * ng : nullptr, jac ? w.jac + p0 * nj : nullptr,
+                      hess ? w.hess + p0 * nh : nullptr, scr, st))
+      return 1;
+    if (f) CK(cudaMemcpyAsync(f + p0, w.f + p0, Bc * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (grad_f) CK(cudaMemcpyAsync(grad_f + p0 * nw, w.grad_f + p0 * nw, Bc * nw * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (g) CK(cudaMemcpyAsync(g + p0 * ng, w.g + p0 * ng, Bc * ng * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (jac) CK(cudaMemcpyAsync(jac + p0 * nj, w.jac + p0 * nj, Bc * nj * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (hess) CK(cudaMemcpyAsync(hess + p0 * nh, w.hess + p0 * nh, Bc * nh * sizeof(double), cudaMemcpyDeviceToHost, st));
   }
-  if (rb_eval_batch(p, B, w.x, dl, dlf, w.vp, p->nvp, nullptr, f ? w.f : nullptr, grad_f ? w.grad_f : nullptr,
-                    g ? w.g : nullptr, jac ? w.jac : nullptr, hess ? w.hess : nullptr, w.scratch, st))
-    return 1;
-  if (f) CK(cudaMemcpyAsync(f, w.f, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (grad_f) CK(cudaMemcpyAsync(grad_f, w.grad_f, (size_t)B * d.nw * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (g) CK(cudaMemcpyAsync(g, w.g, (size_t)B * d.ng * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (jac) CK(cudaMemcpyAsync(jac, w.jac, (size_t)B * d.nnzj * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (hess) CK(cudaMemcpyAsync(hess, w.hess, (size_t)B * d.nnzh * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  CK(cudaStreamSynchronize(w.stream));
+  CK(cudaStreamSynchronize(w.stream2));
   return 0;
 }
 
