@@ -393,8 +393,9 @@ size_t rb_eval_scratch_bytes(const rb_problem* p, int B) {
 int rb_eval_batch(const rb_problem* p, int B, const double* x, const double* lam_g, const double* lam_f,
                   const double* vp, int vp_stride, const double* fc_b, double* f, double* grad_f,
                   double* g, double* jac, double* hess, void* scratch, void* stream) {
-  if (!p || !x || !vp) return fail("rb_eval_batch: null problem / x / vp");
-  if (B <= 0) return 0;
+  if (!p) return fail("rb_eval_batch: null problem");
+  if (B <= 0) return 0;     // an empty batch is a no-op
+  if (!x || !vp) return fail("rb_eval_batch: null x / vp");
   if (hess && !lam_g && p->d.ng > 0) return fail("rb_eval_batch: hess requested without lam_g");
   if ((f || p->d.transcription == RB_RK4) && !scratch) return fail("rb_eval_batch: scratch buffer required");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -516,8 +517,9 @@ int rb_fp64_peak(double* tflops) {
 // ---- host-buffer entry points -------------------------------------------------------------------
 static int host_eval(const rb_problem* cp, int B, const double* x, const double* vp, const double* lam_f,
                      const double* lam_g, double* f, double* grad_f, double* g, double* jac, double* hess) {
-  if (!cp || !x || !vp) return fail("null problem / x / vp");
-  if (B <= 0) return 0;
+  if (!cp) return fail("null problem");
+  if (B <= 0) return 0;     // an empty batch is a no-op
+  if (!x || !vp) return fail("null x / vp");
   rb_problem* p = const_cast<rb_problem*>(cp);
   std::lock_guard<std::mutex> lock(p->mu);
   if (ensure_ws(p, B)) return 1;
