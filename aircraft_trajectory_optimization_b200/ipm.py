@@ -67,6 +67,9 @@ class IpmOptions:
     delta_c_bar: float = 1e-8
     kappa_c: float = 0.25
     refine_steps: int = 2
+    compact: bool = True               # copy the surviving instances into smaller tensors once few are left
+    compact_frac: float = 0.5
+    compact_min: int = 16
     window: int = 0                    # > 0: at most this many instances iterate at a time; finished ones are
                                        # replaced from the pending queue (keeps the batched kernels full)
     verbose: bool = False
@@ -259,9 +262,48 @@ class InteriorPoint:
             filt_phi[mask, 0] = -float('inf')
             filt_n[mask] = 1
 
+        # ---- physical compaction: once most instances have finished, the survivors are copied into smaller tensors so
+        # that the elementwise work of a sweep scales with what is still iterating, not with the original batch
+        B0 = B
+        orig = torch.arange(B, device=dev)
+        OUT = {}
+
+        def stash(rows_local):
+            ''' park the final state of finished instances (local row indices) in the full-size result arrays '''
+            if not OUT:
+                OUT.update(x=torch.empty(B0, n, dtype=dt, device=dev), f=torch.empty(B0, dtype=dt, device=dev),
+                           g=torch.empty(B0, m, dtype=dt, device=dev), lam_g=torch.empty(B0, m, dtype=dt, device=dev),
+                           lam_x=torch.empty(B0, n, dtype=dt, device=dev), err=torch.empty(B0, dtype=dt, device=dev),
+                           status=torch.empty(B0, dtype=torch.long, device=dev),
+                           iters=torch.empty(B0, dtype=torch.long, device=dev),
+                           n_fact=torch.empty(B0, dtype=torch.long, device=dev))
+            if rows_local.numel() == 0:
+                return
+            dst = orig[rows_local]
+            e_fin = error_at(error_parts(ev, x, s, y, zL, zU, vL, vU), torch.zeros_like(mu))[0]
+            for key, src in (('x', x), ('f', ev['f']), ('g', ev['g']), ('lam_g', y), ('lam_x', zU - zL), ('err', e_fin),
+                             ('status', status), ('iters', iters), ('n_fact', n_fact)):
+                OUT[key][dst] = src[rows_local]
+
         it = 0
         while True:
             active = status == -1
+            n_live = int(((status == -1) | (status == -2)).sum())
+            if o.compact and B > o.compact_min and n_live <= o.compact_frac * B and n_live > 0:
+                live = (status == -1) | (status == -2)
+                stash(torch.nonzero(~live).squeeze(1))
+                keep = torch.nonzero(live).squeeze(1)
+                sel = lambda t_: t_[keep].contiguous()
+                (x, s, y, zL, zU, vL, vU, mu, filt_theta, filt_phi, filt_n, theta_max, theta_min, delta_w_last, delta_w,
+                 delta_c, first_try, attempts, n_fact, status, iters, acc_count, ls_fail, orig, ones_B, zero_h) = map(sel, (
+                     x, s, y, zL, zU, vL, vU, mu, filt_theta, filt_phi, filt_n, theta_max, theta_min, delta_w_last, delta_w,
+                     delta_c, first_try, attempts, n_fact, status, iters, acc_count, ls_fail, orig, ones_B, zero_h))
+                (xL, xU, sL, sU, ceq, eq, ineq, fL, fU, sfL, sfU, dampL, dampU, sdampL, sdampU, n_bounds) = map(sel, (
+                    xL, xU, sL, sU, ceq, eq, ineq, fL, fU, sfL, sfU, dampL, dampU, sdampL, sdampU, n_bounds))
+                ev = {k_: sel(v_) for k_, v_ in ev.items()}
+                be.select(keep)
+                B = keep.numel()
+                active = status == -1
             # ---- convergence and barrier update --------------------------------------------------------
             parts = error_parts(ev, x, s, y, zL, zU, vL, vU)
             E0, dual0, prim0, comp0 = error_at(parts, torch.zeros_like(mu))
@@ -472,12 +514,20 @@ class InteriorPoint:
                 ev = evaluate(x, y, True, active & moved)
 
         status[status < 0] = 2
-        E0 = errors(ev, x, s, y, zL, zU, vL, vU, torch.zeros_like(mu))[0]
-        res.x, res.f, res.g, res.lam_g = x, ev['f'], ev['g'], y
-        res.lam_x = zU - zL
-        res.status, res.success, res.iterations, res.kkt_error = status, status <= 1, iters, E0
+        if OUT:
+            stash(torch.arange(B, device=dev))
+            res.x, res.f, res.g, res.lam_g, res.lam_x = OUT['x'], OUT['f'], OUT['g'], OUT['lam_g'], OUT['lam_x']
+            res.status, res.iterations, res.kkt_error = OUT['status'], OUT['iters'], OUT['err']
+            res.factorisations_each = OUT['n_fact'].cpu().numpy()
+            be.select(None)
+        else:
+            E0 = errors(ev, x, s, y, zL, zU, vL, vU, torch.zeros_like(mu))[0]
+            res.x, res.f, res.g, res.lam_g = x, ev['f'], ev['g'], y
+            res.lam_x = zU - zL
+            res.status, res.iterations, res.kkt_error = status, iters, E0
+            res.factorisations_each = n_fact.cpu().numpy()
+        res.success = res.status <= 1
         res.n_iter = it
-        res.factorisations_each = n_fact.cpu().numpy()
         res.t_total = time.perf_counter() - t_start
         return res
 
@@ -491,6 +541,7 @@ class CudaBackend:
         self.st = functions.st
         self.ng = self.st.ng
         self.vp = vp                                   # device tensor (nvp,) or (B, nvp)
+        self._vp_full = vp
         self.K = kkt_solver or KktSolver(self.st)
         self.refine_tol = 1e-10
         self._buf = {}
@@ -501,6 +552,16 @@ class CudaBackend:
             t = torch.empty(shape, dtype=torch.float64, device=dev)
             self._buf[name] = t
         return t
+
+    def select(self, keep):
+        ''' the driver compacted its state to the instances `keep` (None: back to the full batch) '''
+        if keep is None:
+            self.vp = self._vp_full
+        elif self.vp.dim() == 2:
+            if getattr(self, '_vp_full', None) is None:
+                self._vp_full = self.vp
+            self.vp = self.vp[keep].contiguous()
+        self._buf = {}
 
     def _vp_rows(self, idx):
         return self.vp if (idx is None or self.vp.dim() == 1) else self.vp[idx].contiguous()

@@ -57,6 +57,7 @@ class InteriorPointSolver:
         if self._backend is None:
             self._backend = CudaBackend(F, vp)
         self._backend.vp = vp.contiguous()
+        self._backend._vp_full = self._backend.vp
         opts = self.options or IpmOptions()
         opts.max_iter = self.max_iter
         opts.verbose = bool(self.verbose) and single

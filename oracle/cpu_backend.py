@@ -43,6 +43,9 @@ class OracleBackend:
         return dict(f=T(gf[:, 0].copy()), grad_f=T(gf[:, 1:].copy()), g=T(jg[:, :nlp.ng].copy()),
                     jac=T(jg[:, nlp.ng:].copy()), hess=T(h))
 
+    def select(self, keep):
+        pass
+
     def eval_points(self, x_rows, inst):
         out = self.eval(x_rows, None, None, False)
         return dict(f=out['f'], g=out['g'])

@@ -62,3 +62,26 @@ def test_golden_solutions_are_kkt_points():
         prod, ref = build_case(name, N=N)
         gold = np.load(os.path.join(GOLD, f'ipm_{name}_N{N}.npz'))
         _kkt_conditions(prod.structure, OracleNLP(ref, build_hess=False), gold['x'], gold['lam_g'], gold['lam_x'])
+
+
+def test_compaction_and_window_do_not_change_results():
+    ''' instances that finish early are compacted away / refilled from the queue; every instance's answer is unchanged '''
+    from oracle.nlp_functions import OracleNLP
+    from oracle.cpu_backend import OracleBackend
+    from aircraft_trajectory_optimization_b200.ipm import InteriorPoint, IpmOptions
+    from aircraft_trajectory_optimization_b200.kkt import build_kkt_structure
+    prod, ref = build_case('race_global_rk4_point', N=7)
+    st = prod.structure
+    nlp = OracleNLP(ref)
+    be = OracleBackend(nlp, nlp, ks=build_kkt_structure(st))
+    T = lambda a: torch.from_numpy(np.asarray(a, dtype=float))
+    rng = np.random.default_rng(0)
+    X0 = np.tile(st.w0, (3, 1))
+    X0[1] += 0.02 * rng.standard_normal(st.nw)
+    X0[2] += 0.05 * rng.standard_normal(st.nw)
+    args = (T(X0), T(st.lbw), T(st.ubw), T(st.lbg), T(st.ubg))
+    base = InteriorPoint(be, IpmOptions(max_iter=150, compact=False)).solve(*args)
+    comp = InteriorPoint(be, IpmOptions(max_iter=150, compact=True, compact_min=1, compact_frac=0.7, window=2)).solve(*args)
+    assert base.success.all() and len(set(base.iterations.tolist())) > 1      # they finish at different times
+    assert torch.equal(base.status, comp.status) and torch.equal(base.iterations, comp.iterations)
+    assert torch.equal(base.x, comp.x) and torch.equal(base.lam_g, comp.lam_g) and torch.equal(base.lam_x, comp.lam_x)
