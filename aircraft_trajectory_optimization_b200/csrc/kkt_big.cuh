@@ -252,8 +252,8 @@ kkt_factor_solve_big_kernel(const RbKktDev d, const RbKktBatch bt, double* __res
             bt.neg_d + (size_t)p * d.ng};
   const double* __restrict__ rhs = bt.rhs + (size_t)p * nk;
   double* __restrict__ sol = bt.sol + (size_t)p * nk;
-  double* __restrict__ Sinv_g = bt.Sinv + (size_t)p * N * bmax * bmax;
-  double* __restrict__ YL_g = bt.YL + (size_t)p * N * bmax * mmax;
+  double* __restrict__ Sinv_g = bt.Sinv + (size_t)p * N * bmax * d.ldS;
+  double* __restrict__ YL_g = bt.YL + (size_t)p * N * bmax * d.ldY;
   double* __restrict__ X_g = bt.X + (size_t)p * N * bmax * nrhs;
   double* __restrict__ Yr = work + (size_t)p * work_stride;       // [nbb][nrhs]
   double* __restrict__ Zs = Yr + (size_t)nbb * nrhs;              // [nbb][nrhs]
@@ -267,12 +267,16 @@ kkt_factor_solve_big_kernel(const RbKktDev d, const RbKktBatch bt, double* __res
   for (int n = 0; n < N; ++n) {
     const int u0 = d.blk_ptr[n], b = d.blk_ptr[n + 1] - u0;
     const int32_t* __restrict__ unk = d.unk + u0;
-    double* __restrict__ M = Sinv_g + (size_t)n * bmax * bmax;    // inverted in place, leading dimension bmax
-    const int LD = bmax;
+    double* __restrict__ M = Sinv_g + (size_t)n * bmax * d.ldS;   // inverted in place, leading dimension ldS
+    const int LD = d.ldS;
     for (int i = tid; i < b * LD; i += nthreads) M[i] = 0.0;
     for (int i = tid; i < b * nrhs; i += nthreads) Yr[i] = 0.0;
     __syncthreads();
-    for (int e = d.dA_ptr[n] + tid; e < d.dA_ptr[n + 1]; e += nthreads) M[d.dA_pos[e]] = kkt_val(v, d.dA_src[e]);
+    for (int e = d.dA_ptr[n] + tid; e < d.dA_ptr[n + 1]; e += nthreads) {
+      const int pos = d.dA_pos[e];
+      const int r = pos / bmax, c = pos - r * bmax;
+      M[(size_t)r * LD + c] = kkt_val(v, d.dA_src[e]);
+    }
     for (int e = d.bE_ptr[n] + tid; e < d.bE_ptr[n + 1]; e += nthreads)
       Yr[(size_t)d.bE_row[e] * nrhs + 1 + d.bE_col[e]] = kkt_val(v, d.bE_src[e]);
     __syncthreads();
@@ -308,7 +312,7 @@ kkt_factor_solve_big_kernel(const RbKktDev d, const RbKktBatch bt, double* __res
         double acc = 0.0;
         for (int t = 0; t < q; ++t) acc += M[(size_t)r * LD + cc[t]] * s.Lc[a * qmax + t];
         YLs[(size_t)r * mmax + a] = acc;
-        YL_g[((size_t)n * bmax + r) * mmax + a] = acc;
+        YL_g[((size_t)n * bmax + r) * d.ldY + a] = acc;
       }
       __syncthreads();
       for (int i = tid; i < m * m; i += nthreads) {
@@ -344,7 +348,7 @@ kkt_factor_solve_big_kernel(const RbKktDev d, const RbKktBatch bt, double* __res
     __syncthreads();
     for (int i = tid; i < b * nrhs; i += nthreads) {
       const int row = i / nrhs, r = i - row * nrhs;
-      const double* __restrict__ yl = YL_g + ((size_t)n * bmax + row) * mmax;
+      const double* __restrict__ yl = YL_g + ((size_t)n * bmax + row) * d.ldY;
       double acc = X_g[((size_t)n * bmax + row) * nrhs + r];
       for (int a = 0; a < m; ++a) acc -= yl[a] * s.rcarry[a * nrhs + r];
       nxt[(size_t)row * nrhs + r] = acc;

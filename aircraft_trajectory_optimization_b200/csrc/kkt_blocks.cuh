@@ -23,6 +23,8 @@
 
 struct RbKktDev {
   int nw, ng, N, nb, bmax, mmax, qmax, n_bG;
+  int ldS, ldY;   // row strides of the stored block inverses / coupling solves: bmax, mmax rounded up to even, so that
+                  // every block of the factor storage is a 16-byte multiple (TMA bulk copies in the re-solve)
   const int32_t *blk_ptr, *unk;
   const int32_t *dA_ptr, *dA_src, *dA_pos;
   const int32_t *cr_ptr, *cr, *cc_ptr, *cc, *cL_ptr, *cL_src, *cL_pos;
@@ -319,8 +321,8 @@ kkt_factor_solve_kernel(const RbKktDev d, const RbKktBatch bt) {
             bt.neg_d + (size_t)p * d.ng};
   const double* __restrict__ rhs = bt.rhs + (size_t)p * nk;
   double* __restrict__ sol = bt.sol + (size_t)p * nk;
-  double* __restrict__ Sinv_g = bt.Sinv + (size_t)p * N * bmax * bmax;
-  double* __restrict__ YL_g = bt.YL + (size_t)p * N * bmax * mmax;
+  double* __restrict__ Sinv_g = bt.Sinv + (size_t)p * N * bmax * d.ldS;
+  double* __restrict__ YL_g = bt.YL + (size_t)p * N * bmax * d.ldY;
   double* __restrict__ X_g = bt.X + (size_t)p * N * bmax * nrhs;
   int bad = 0, neg = 0;
   int m_prev = 0;
@@ -395,7 +397,7 @@ kkt_factor_solve_kernel(const RbKktDev d, const RbKktBatch bt) {
     // keep the inverse
     if (bt.Sinv) {
       for (int i = warp; i < b; i += nwarps)
-        for (int j = lane; j < b; j += 32) Sinv_g[((size_t)n * bmax + i) * bmax + j] = s.M[i * LD + j];
+        for (int j = lane; j < b; j += 32) Sinv_g[((size_t)n * bmax + i) * d.ldS + j] = s.M[i * LD + j];
     }
     if (n < N - 1) {
       const int m = d.cr_ptr[n + 1] - d.cr_ptr[n], q = d.cc_ptr[n + 1] - d.cc_ptr[n];
@@ -410,7 +412,7 @@ kkt_factor_solve_kernel(const RbKktDev d, const RbKktBatch bt) {
           double acc = 0.0;
           for (int t = 0; t < q; ++t) acc += s.M[i * LD + cc[t]] * s.Lc[a * qmax + t];
           s.YLs[i * mmax + a] = acc;
-          YL_g[((size_t)n * bmax + i) * mmax + a] = acc;
+          YL_g[((size_t)n * bmax + i) * d.ldY + a] = acc;
         }
       }
       __syncthreads();
@@ -454,8 +456,8 @@ kkt_factor_solve_kernel(const RbKktDev d, const RbKktBatch bt) {
         int rc[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) rc[c] = (tc_ + c * nct < nrhs) ? tc_ + c * nct : tc_;
-        const double* __restrict__ y0 = YL_g + ((size_t)n * bmax + i0) * mmax;
-        const double* __restrict__ y1 = YL_g + ((size_t)n * bmax + i1) * mmax;
+        const double* __restrict__ y0 = YL_g + ((size_t)n * bmax + i0) * d.ldY;
+        const double* __restrict__ y1 = YL_g + ((size_t)n * bmax + i1) * d.ldY;
         double acc[2][4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -574,8 +576,8 @@ kkt_resolve_kernel(const RbKktDev d, const RbKktBatch bt) {
             bt.neg_d + (size_t)p * d.ng};
   const double* __restrict__ rhs = bt.rhs + (size_t)p * nk;
   double* __restrict__ sol = bt.sol + (size_t)p * nk;
-  const double* __restrict__ Sinv_g = bt.Sinv + (size_t)p * N * bmax * bmax;
-  const double* __restrict__ YL_g = bt.YL + (size_t)p * N * bmax * mmax;
+  const double* __restrict__ Sinv_g = bt.Sinv + (size_t)p * N * bmax * d.ldS;
+  const double* __restrict__ YL_g = bt.YL + (size_t)p * N * bmax * d.ldY;
   const double* __restrict__ X_g = bt.X + (size_t)p * N * bmax * nrhs;
   double* __restrict__ Xr = bt.Xr + (size_t)p * N * bmax;
   int m_prev = 0;
@@ -589,7 +591,7 @@ kkt_resolve_kernel(const RbKktDev d, const RbKktBatch bt) {
       __syncthreads();
     }
     for (int i = tid; i < b; i += blockDim.x) {
-      const double* __restrict__ si = Sinv_g + ((size_t)n * bmax + i) * bmax;
+      const double* __restrict__ si = Sinv_g + ((size_t)n * bmax + i) * d.ldS;
       double acc = 0.0;
       for (int j = 0; j < b; ++j) acc += si[j] * y[j];
       Xr[(size_t)n * bmax + i] = acc;
@@ -599,7 +601,7 @@ kkt_resolve_kernel(const RbKktDev d, const RbKktBatch bt) {
       // L_n S_n^-1 y_n = YL_n' y_n   (S_n is symmetric)
       for (int a = tid; a < m; a += blockDim.x) {
         double acc = 0.0;
-        for (int i = 0; i < b; ++i) acc += YL_g[((size_t)n * bmax + i) * mmax + a] * y[i];
+        for (int i = 0; i < b; ++i) acc += YL_g[((size_t)n * bmax + i) * d.ldY + a] * y[i];
         rc[a] = acc;
       }
       m_prev = m;
@@ -619,12 +621,190 @@ kkt_resolve_kernel(const RbKktDev d, const RbKktBatch bt) {
     for (int a = tid; a < m; a += blockDim.x) rc[a] = xn[cr[a]];
     __syncthreads();
     for (int i = tid; i < b; i += blockDim.x) {
-      const double* __restrict__ yl = YL_g + ((size_t)n * bmax + i) * mmax;
+      const double* __restrict__ yl = YL_g + ((size_t)n * bmax + i) * d.ldY;
       double acc = Xr[(size_t)n * bmax + i];
       for (int a = 0; a < m; ++a) acc -= yl[a] * rc[a];
       xn[i] = acc;
       Xr[(size_t)n * bmax + i] = acc;
     }
+    __syncthreads();
+  }
+  if (nb > 0) {
+    const int32_t* __restrict__ unkb = d.unk + d.blk_ptr[N];
+    for (int j = tid; j < nb; j += blockDim.x) {
+      double acc = rhs[unkb[j]];
+      for (int t = d.bEc_ptr[j]; t < d.bEc_ptr[j + 1]; ++t) {
+        const int e = d.bEc_idx[t];
+        acc -= kkt_val(v, d.bE_src[e]) * Xr[(size_t)d.bE_blk[e] * bmax + d.bE_row[e]];
+      }
+      y[j] = acc;
+    }
+    __syncthreads();
+    for (int i = tid; i < nb; i += blockDim.x) {
+      double acc = 0.0;
+      for (int j = 0; j < nb; ++j) acc += bt.SB[(size_t)p * nb * nb + i * nb + j] * y[j];
+      xb[i] = acc;
+      sol[unkb[i]] = acc;
+    }
+    __syncthreads();
+  }
+  const int nchain = d.blk_ptr[N];
+  for (int t = tid; t < nchain; t += blockDim.x) {
+    int lo = 0, hi = N - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (d.blk_ptr[mid] <= t) lo = mid; else hi = mid - 1;
+    }
+    const int i = t - d.blk_ptr[lo];
+    const double* __restrict__ x = X_g + ((size_t)lo * bmax + i) * nrhs;
+    double acc = Xr[(size_t)lo * bmax + i];
+    for (int j = 0; j < nb; ++j) acc -= x[1 + j] * xb[j];
+    sol[d.unk[t]] = acc;
+  }
+}
+
+// The same re-solve for stage blocks that fit shared memory: the block inverse S_n^-1 and the coupling solve YL_n
+// of the next block are fetched by TMA bulk copies (cp.async.bulk + mbarrier, double-buffered) while the current
+// block is applied, so the sequential walk over the chain is not exposed to global-memory latency; eight threads
+// share every row of the matrix-vector products.
+__global__ void __launch_bounds__(RB_KKT_THREADS)
+kkt_resolve_tma_kernel(const RbKktDev d, const RbKktBatch bt) {
+  extern __shared__ __align__(128) double kkt_smem[];
+  __shared__ __align__(8) unsigned long long bars[2];
+  const int p = blockIdx.x;
+  if (p >= bt.B) return;
+  const int tid = threadIdx.x;
+  const int nk = d.nw + d.ng, nrhs = 1 + d.nb, bmax = d.bmax, mmax = d.mmax, N = d.N, nb = d.nb;
+  const int nbb = nb > bmax ? nb : bmax;
+  const int SZ_S = bmax * d.ldS, SZ_Y = bmax * d.ldY;                // doubles per block of the two factor arrays (even)
+  const int BUF = SZ_S + SZ_Y;
+  double* buf0 = kkt_smem;
+  double* y = kkt_smem + 2 * BUF;     // [nbb] current block rhs
+  double* xn = y + nbb;               // [nbb] solution of the block above (backward)
+  double* rc = xn + nbb;              // [mmax] carry
+  double* xb = rc + mmax;             // [nb]
+  KktVals v{bt.hess + (size_t)p * bt.nnzh, bt.jac + (size_t)p * bt.nnzj, bt.dx_diag + (size_t)p * d.nw,
+            bt.neg_d + (size_t)p * d.ng};
+  const double* __restrict__ rhs = bt.rhs + (size_t)p * nk;
+  double* __restrict__ sol = bt.sol + (size_t)p * nk;
+  const double* __restrict__ Sinv_g = bt.Sinv + (size_t)p * N * SZ_S;
+  const double* __restrict__ YL_g = bt.YL + (size_t)p * N * SZ_Y;
+  const double* __restrict__ X_g = bt.X + (size_t)p * N * bmax * nrhs;
+  double* __restrict__ Xr = bt.Xr + (size_t)p * N * bmax;
+
+  auto issue = [&](int step, int n, bool with_s) {
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&bars[step & 1]);
+    double* dstS = buf0 + (size_t)(step & 1) * BUF;
+    const unsigned bytes = (unsigned)((with_s ? SZ_S : 0) + SZ_Y) * 8u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    if (with_s)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       (unsigned)__cvta_generic_to_shared(dstS)),
+                   "l"(Sinv_g + (size_t)n * SZ_S), "r"((unsigned)SZ_S * 8u), "r"(bar)
+                   : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(dstS + SZ_S)),
+                 "l"(YL_g + (size_t)n * SZ_Y), "r"((unsigned)SZ_Y * 8u), "r"(bar)
+                 : "memory");
+  };
+  auto wait = [&](int step) {
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&bars[step & 1]);
+    const unsigned parity = (step >> 1) & 1;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "KKTR_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra KKTR_DONE_%=;\n"
+        "bra KKTR_WAIT_%=;\n"
+        "KKTR_DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+  };
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&bars[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&bars[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // steps 0..N-1: forward over blocks 0..N-1 (S^-1 and YL); steps N..2N-2: backward over blocks N-2..0 (YL only)
+  const int nsteps = 2 * N - 1;
+  auto block_of = [&](int step) { return step < N ? step : 2 * N - 2 - step; };
+  if (tid == 0) {
+    issue(0, block_of(0), true);
+    if (nsteps > 1) issue(1, block_of(1), 1 < N);
+  }
+  const int grp = tid >> 3, part = tid & 7;          // eight threads per row of a product
+  int m_prev = 0;
+  const int32_t* cr_prev = nullptr;
+  for (int n = 0; n < N; ++n) {
+    const int step = n;
+    const int u0 = d.blk_ptr[n], b = d.blk_ptr[n + 1] - u0;
+    for (int i = tid; i < b; i += blockDim.x) y[i] = rhs[d.unk[u0 + i]];
+    __syncthreads();
+    if (n > 0) {
+      for (int a = tid; a < m_prev; a += blockDim.x) y[cr_prev[a]] -= rc[a];
+      __syncthreads();
+    }
+    wait(step);
+    const double* __restrict__ Sn = buf0 + (size_t)(step & 1) * BUF;
+    const double* __restrict__ Yn = Sn + SZ_S;
+    // (loop bounds are uniform over the block: every lane takes part in the shuffles)
+    for (int ib = 0; ib < b; ib += RB_KKT_THREADS / 8) {
+      const int i = ib + grp;
+      double acc = 0.0;
+      if (i < b)
+        for (int j = part; j < b; j += 8) acc += Sn[i * d.ldS + j] * y[j];
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (part == 0 && i < b) Xr[(size_t)n * bmax + i] = acc;
+    }
+    if (n < N - 1) {
+      const int m = d.cr_ptr[n + 1] - d.cr_ptr[n];
+      // L_n S_n^-1 y_n = YL_n' y_n   (S_n is symmetric)
+      for (int ab = 0; ab < m; ab += RB_KKT_THREADS / 8) {
+        const int a = ab + grp;
+        double acc = 0.0;
+        if (a < m)
+          for (int i = part; i < b; i += 8) acc += Yn[i * d.ldY + a] * y[i];
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if (part == 0 && a < m) rc[a] = acc;
+      }
+      m_prev = m;
+      cr_prev = d.cr + d.cr_ptr[n];
+    }
+    __syncthreads();                                   // this buffer and y are free again
+    if (tid == 0 && step + 2 < nsteps) issue(step + 2, block_of(step + 2), step + 2 < N);
+  }
+  {
+    const int b = d.blk_ptr[N] - d.blk_ptr[N - 1];
+    for (int i = tid; i < b; i += blockDim.x) xn[i] = Xr[(size_t)(N - 1) * bmax + i];
+    __syncthreads();
+  }
+  for (int n = N - 2; n >= 0; --n) {
+    const int step = 2 * N - 2 - n;
+    const int b = d.blk_ptr[n + 1] - d.blk_ptr[n];
+    const int m = d.cr_ptr[n + 1] - d.cr_ptr[n];
+    const int32_t* __restrict__ cr = d.cr + d.cr_ptr[n];
+    for (int a = tid; a < m; a += blockDim.x) rc[a] = xn[cr[a]];
+    wait(step);
+    __syncthreads();
+    const double* __restrict__ Yn = buf0 + (size_t)(step & 1) * BUF + SZ_S;
+    for (int i = tid; i < b; i += blockDim.x) {
+      double acc = Xr[(size_t)n * bmax + i];
+      for (int a = 0; a < m; ++a) acc -= Yn[i * d.ldY + a] * rc[a];
+      y[i] = acc;
+    }
+    __syncthreads();
+    for (int i = tid; i < b; i += blockDim.x) {
+      xn[i] = y[i];
+      Xr[(size_t)n * bmax + i] = y[i];
+    }
+    if (tid == 0 && step + 2 < nsteps) issue(step + 2, block_of(step + 2), false);
     __syncthreads();
   }
   if (nb > 0) {
