@@ -205,33 +205,41 @@ def generate_variant(variant: Variant, out_dir=GEN_DIR):
         + [f'Hst[th[{i}]]' for i in range(len(pf.W))])
     parts.append(code)
     # ---- materialised form for the two-kernel shooting path (csrc/rk4_cells.cuh) ------------------
-    # fJ_s / vjpW_s write the non-zeros of J and W straight into a strided scratch column (stride SCR_STRIDE);
+    # fJ_s / vjpW_s write the non-zeros of J and W straight into a strided scratch column: entries are stored in
+    # pairs (2i, 2i+1) adjacent, pair i of a cell at double offset 2 * i * SCR_STRIDE, so that the direction
+    # threads read two entries with one 16-byte shared-memory load (one load per two multiply-adds);
     # jmul / jtmul / wmul are the sparse products the direction threads run against those columns.
     code, ops['fJ_s'] = _emit_fn(pf, 'fJ_s', [cx, cfc, cvp, 'double* __restrict__ f', 'double* __restrict__ Js'],
                                  pf.f + pf.J_nodes,
-                                 [f'f[{i}]' for i in range(nz)] + [f'Js[{i} * SCR_STRIDE]' for i in range(len(pf.J))])
+                                 [f'f[{i}]' for i in range(nz)] + [f'Js[{(i >> 1) * 2} * SCR_STRIDE + {i & 1}]' for i in range(len(pf.J))])
     parts.append(code)
     code, ops['vjpW_s'] = _emit_fn(pf, 'vjpW_s', [cx, 'const double* __restrict__ kb', cfc, cvp,
                                                   'double* __restrict__ xb', 'double* __restrict__ Ws'],
                                    pf.xb + pf.W_nodes,
-                                   [f'xb[{i}]' for i in range(nx)] + [f'Ws[{i} * SCR_STRIDE]' for i in range(len(pf.W))])
+                                   [f'xb[{i}]' for i in range(nx)] + [f'Ws[{(i >> 1) * 2} * SCR_STRIDE + {i & 1}]' for i in range(len(pf.W))])
     parts.append(code)
 
-    def sparse_product(fname, sig, lines_fn, nops):
-        body = '\n'.join('    ' + ln for ln in lines_fn())
+    def sparse_product(fname, sig, lines_fn, nops, src, n_ent):
+        loads = [f'const double2* __restrict__ P2 = reinterpret_cast<const double2*>({src});'] if n_ent else \
+            [f'(void){src};']
+        loads += [f'const double2 q{i} = P2[{i} * SCR_STRIDE];' for i in range((n_ent + 1) // 2)]
+        body = '\n'.join('    ' + ln for ln in loads + lines_fn())
         return (f'  // {nops} multiply-adds\n  __device__ __forceinline__ static void {fname}({sig}) {{\n{body}\n  }}\n')
+
+    def ent(e):
+        return f'q{e >> 1}.{"xy"[e & 1]}'
 
     def jmul_lines():
         out = []
         for r in range(nz):
-            terms = [f'Js[{e} * SCR_STRIDE] * dx[{c}]' for e, (rr, c) in enumerate(pf.J) if rr == r]
+            terms = [f'{ent(e)} * dx[{c}]' for e, (rr, c) in enumerate(pf.J) if rr == r]
             out.append(f'dk[{r}] = ' + (' + '.join(terms) if terms else '0.0') + ';')
         return out
 
     def jtmul_lines():
         out = []
         for c in range(nx):
-            terms = [f'Js[{e} * SCR_STRIDE] * dkb[{r}]' for e, (r, cc) in enumerate(pf.J) if cc == c]
+            terms = [f'{ent(e)} * dkb[{r}]' for e, (r, cc) in enumerate(pf.J) if cc == c]
             if terms:
                 out.append(f'dxb[{c}] += ' + ' + '.join(terms) + ';')
         return out
@@ -242,19 +250,19 @@ def generate_variant(variant: Variant, out_dir=GEN_DIR):
             terms = []
             for e, (r, c) in enumerate(pf.W):
                 if r == i:
-                    terms.append(f'Ws[{e} * SCR_STRIDE] * dx[{c}]')
+                    terms.append(f'{ent(e)} * dx[{c}]')
                 elif c == i:
-                    terms.append(f'Ws[{e} * SCR_STRIDE] * dx[{r}]')
+                    terms.append(f'{ent(e)} * dx[{r}]')
             out.append(f'dxb[{i}] = ' + (' + '.join(terms) if terms else '0.0') + ';')
         return out
 
     cJs, cWs = 'const double* __restrict__ Js', 'const double* __restrict__ Ws'
     parts.append(sparse_product('jmul', f'{cJs}, const double* __restrict__ dx, double* __restrict__ dk',
-                                jmul_lines, len(pf.J)))
+                                jmul_lines, len(pf.J), 'Js', len(pf.J)))
     parts.append(sparse_product('wmul', f'{cWs}, const double* __restrict__ dx, double* __restrict__ dxb',
-                                wmul_lines, 2 * len(pf.W)))
+                                wmul_lines, 2 * len(pf.W), 'Ws', len(pf.W)))
     parts.append(sparse_product('jtmul', f'{cJs}, const double* __restrict__ dkb, double* __restrict__ dxb',
-                                jtmul_lines, len(pf.J)))
+                                jtmul_lines, len(pf.J), 'Js', len(pf.J)))
 
     def table(tname, vals):
         return f'  static constexpr signed char {tname}[{max(len(vals), 1)}] = {{' \
@@ -269,7 +277,8 @@ def generate_variant(variant: Variant, out_dir=GEN_DIR):
            f'NVP = {len(variant.vp_names)};\n'
            f'  static constexpr int NJ = {len(pf.J)}, NW = {len(pf.W)};\n'
            f'  // shooting cells: CPB cells per 128-thread block of the direction kernel; the scratch of a block is\n'
-           f'  // stored entry-major with the CPB cells of the block adjacent (stride of one entry = CPB doubles)\n'
+           f'  // stored entry-major with the CPB cells of the block adjacent (stride of one entry = CPB doubles; J and W\n'
+           f'  // entries in adjacent pairs, stride of one pair = 2 CPB doubles)\n'
            f'  static constexpr int CPB = 128 / ({nx} + 1), SCR_STRIDE = CPB;\n'
            f'  static constexpr bool QUAT = {"true" if variant.vehicle == "drone" and variant.orient == "quat" else "false"};\n'
            f'  static constexpr bool USES_FC = {"true" if variant.parametric else "false"};\n'

@@ -235,6 +235,8 @@ int ensure_ws(rb_problem* p, int B) {
 
 }  // namespace
 
+static void cas_forget(rb_problem* p);
+
 extern "C" {
 
 const char* rb_last_error(void) { return g_err.c_str(); }
@@ -348,6 +350,7 @@ int rb_problem_create(const rb_problem_desc* s, rb_problem** out) {
 }
 
 void rb_problem_destroy(rb_problem* p) {
+  cas_forget(p);   // the CasADi-style symbols must not keep a dangling problem
   if (!p) return;
   for (void* q : p->owned) cudaFree(q);
   cudaStream_t st = p->ws.stream, st2 = p->ws.stream2;
@@ -585,4 +588,5 @@ int rb_nlp_eval_all(const rb_problem* p, int B, const double* x, const double* v
 
 }  // extern "C"
 
+#include "casadi_abi.inc"
 #include "kkt_host.inc"

@@ -27,7 +27,10 @@ struct Rk4Scratch {
   static constexpr int NZ = PF::NZ, NJ = PF::NJ, NW = PF::NW, CPB = PF::CPB;
   // entries of a stage block: J, W, k_i, xb_i (z part), k_{i-1}, xb_{i+1} (z part); padded to an even count so
   // that SB * CPB * 8 bytes is a multiple of 16 (TMA bulk copies)
-  static constexpr int oJ = 0, oW = NJ, oK = NJ + NW, oX = oK + NZ, oKp = oX + NZ, oXn = oKp + NZ;
+  // J and W are stored in pairs (entries 2i, 2i+1 of a cell adjacent; pair i of local cell lc at double
+  // offset (i * CPB + lc) * 2 of the region), everything else one double per (entry, cell)
+  static constexpr int NJP = (NJ + 1) / 2 * 2, NWP = (NW + 1) / 2 * 2;
+  static constexpr int oJ = 0, oW = NJP, oK = NJP + NWP, oX = oK + NZ, oKp = oX + NZ, oXn = oKp + NZ;
   static constexpr int SB = (oXn + NZ + 1) / 2 * 2;
   static constexpr int NS = 4 * SB;                  // doubles per cell
   static constexpr int STAGE_DOUBLES = SB * CPB;     // doubles per (group, stage) block
@@ -71,8 +74,9 @@ rk4_point_kernel(const RbDev d, const RbBatch b, double* __restrict__ scr) {
   const double* __restrict__ fcp =
       PF::USES_FC ? (b.fc_b ? b.fc_b + (size_t)p * d.N * PF::NFC : d.fc) + (size_t)n * PF::NFC : d.fc;
   const double* __restrict__ vpp = b.vp + (size_t)p * b.vp_stride;
-  // entry e of stage st of this cell: S[(st * SB + e) * CPB]
-  double* __restrict__ S = scr + (size_t)(cell / CPB) * SC::NS * CPB + (cell % CPB);
+  // entry e of stage st of this cell: S[(st * SB + e) * CPB]; pair i of J / W: (S - lc)[(st * SB + o) * CPB + 2 * (i * CPB + lc)]
+  const int lc = (int)(cell % CPB);
+  double* __restrict__ S = scr + (size_t)(cell / CPB) * SC::NS * CPB + lc;
 
   double x1[NX], xs[NX], k[NZ], Ks[NZ];
 #pragma unroll
@@ -91,7 +95,7 @@ rk4_point_kernel(const RbDev d, const RbBatch b, double* __restrict__ scr) {
     double* __restrict__ Sst = S + (size_t)st * SC::SB * CPB;
 #pragma unroll
     for (int i = 0; i < NZ; ++i) Sst[(SC::oKp + i) * CPB] = k[i];          // k_{st-1} (zero for the first stage)
-    PF::fJ_s(xs, fcp, vpp, k, Sst + SC::oJ * CPB);
+    PF::fJ_s(xs, fcp, vpp, k, Sst + SC::oJ * CPB + lc);
     const double bw = (st == 0 || st == 3) ? 1.0 : 2.0;
     const double an = (st == 2) ? h : 0.5 * h;        // a_{st+2} h
 #pragma unroll
@@ -124,7 +128,7 @@ rk4_point_kernel(const RbDev d, const RbBatch b, double* __restrict__ scr) {
       kb[i] = bw * muz[i] + an * xb[i];
       xs[i] = x1[i] + ax * Sst[(SC::oKp + i) * CPB];
     }
-    PF::vjpW_s(xs, kb, fcp, vpp, xb, Sst + SC::oW * CPB);
+    PF::vjpW_s(xs, kb, fcp, vpp, xb, Sst + SC::oW * CPB + lc);
 #pragma unroll
     for (int i = 0; i < NZ; ++i) Sst[(SC::oX + i) * CPB] = xb[i];
   }
@@ -230,7 +234,7 @@ rk4_dir_kernel(const RbDev d, const RbBatch b, const double* __restrict__ scr) {
   for (int st = 0; st < 4; ++st) {
     wait(st);
     const double* __restrict__ Sst = rk4_smem + (size_t)(st & 1) * SC::STAGE_DOUBLES + lcs;
-    PF::jmul(Sst + SC::oJ * CPB, dxs, dk);
+    PF::jmul(Sst + SC::oJ * CPB + lcs, dxs, dk);
     const double bw = (st == 0 || st == 3) ? 1.0 : 2.0;
     const double an = (st == 2) ? 1.0 : 0.5;
 #pragma unroll
@@ -423,8 +427,8 @@ rk4_dir_kernel(const RbDev d, const RbBatch b, const double* __restrict__ scr) {
       for (int i = 0; i < NZ; ++i)
         dxs[i] = e[i] + ax * (h * dks[((st - 1) * NZ + i) * RB_CELL_THREADS] + dh * Sst[(SC::oKp + i) * CPB]);
     }
-    PF::wmul(Sst + SC::oW * CPB, dxs, dxb);
-    PF::jtmul(Sst + SC::oJ * CPB, dkb, dxb);
+    PF::wmul(Sst + SC::oW * CPB + lcs, dxs, dxb);
+    PF::jtmul(Sst + SC::oJ * CPB + lcs, dkb, dxb);
 #pragma unroll
     for (int i = 0; i < NZ; ++i) gz[i] += dxb[i];
 #pragma unroll

@@ -50,7 +50,12 @@ EXPORTS = ['rb_last_error', 'rb_device_count', 'rb_set_device', 'rb_problem_crea
            'rb_nlp_f', 'rb_nlp_g', 'rb_nlp_grad_f', 'rb_nlp_jac_g', 'rb_nlp_hess_l', 'rb_nlp_eval_all',
            'rb_launch_count', 'rb_profile_enable', 'rb_profile_cell_ms', 'rb_fp64_peak',
            'rb_kkt_create', 'rb_kkt_destroy', 'rb_kkt_factor_bytes', 'rb_kkt_factor_solve', 'rb_kkt_resolve',
-           'rb_kkt_matvec']
+           'rb_kkt_matvec', 'rb_casadi_bind']
+# CasADi generated-code shaped symbols (include/raceline_b200.h, RB_CASADI_DECLARE)
+CASADI_FUNCTIONS = ['nlp_f', 'nlp_g', 'nlp_grad_f', 'nlp_jac_g', 'nlp_hess_l']
+CASADI_SUFFIXES = ['', '_n_in', '_n_out', '_name_in', '_name_out', '_default_in', '_sparsity_in', '_sparsity_out',
+                   '_work', '_alloc_mem', '_init_mem', '_free_mem', '_checkout', '_release', '_incref', '_decref']
+EXPORTS += [f + sfx for f in CASADI_FUNCTIONS for sfx in CASADI_SUFFIXES]
 
 
 def load_library():
@@ -210,6 +215,18 @@ class NlpFunctions:
                                    [dx, dp, d1, dg], [self.sp_hess],
                                    lambda x, p=None, lam_f=1.0, lam_g=None:
                                    (self.eval(x, p, lam_f, lam_g, want='hess')['hess'],))
+
+    def bind_casadi_symbols(self, p=None):
+        ''' make this problem the one the library's CasADi-style symbols (nlp_f, nlp_g, nlp_grad_f, nlp_jac_g,
+        nlp_hess_l and their _n_in / _sparsity_out / ... companions, include/raceline_b200.h) evaluate;
+        p: vehicle parameters used when a caller passes arg[1] == NULL '''
+        vp = self.vp if p is None else p
+        arr = None if vp is None else np.ascontiguousarray(vp, dtype=np.float64)
+        if arr is not None and arr.size != self.nvp:
+            raise ValueError(f'p has {arr.size} entries, expected {self.nvp}')
+        self.lib.rb_casadi_bind.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        _check(self.lib.rb_casadi_bind(self.handle, None if arr is None else arr.ctypes.data_as(ctypes.c_void_p)),
+               'rb_casadi_bind')
 
     def __del__(self):
         try:

@@ -135,6 +135,42 @@ int rb_nlp_hess_l(const rb_problem* p, int B, const double* x, const double* vp,
 int rb_nlp_eval_all(const rb_problem* p, int B, const double* x, const double* vp, const double* lam_f,
                     const double* lam_g, double* f, double* grad_f, double* g, double* jac, double* hess);
 
+/* ---- CasADi generated-code / `external` shaped entry points ----------------------------------------
+ * Replace the five Function objects CasADi's nlpsol derives from prob = {x, g, f, p}
+ * (drone3d/raceline/base_raceline.py:752-799, called inside self.solver(...) at :160-165) with the C
+ * signature CasADi's code generator emits and `ca.external(name, lib)` binds [CasADi, third party]:
+ *     int F(const double** arg, double** res, long long* iw, double* w, int mem)
+ * plus F_n_in/F_n_out, F_name_in/out, F_sparsity_in/out (compressed CCS [nrow, ncol, colind, row]),
+ * F_default_in, F_work and the reference-counting / memory-slot functions.
+ *   nlp_f(x, p) -> f;  nlp_g(x, p) -> g;  nlp_grad_f(x, p) -> (f, grad_f_x);
+ *   nlp_jac_g(x, p) -> (g, jac_g_x);  nlp_hess_l(x, p, lam_f, lam_g) -> triu_hess_gamma_x_x.
+ * arg[i] == NULL reads as zeros (p: the vehicle parameters given at bind time); res[i] == NULL = not
+ * wanted.  CasADi externals carry no context argument: rb_casadi_bind() selects the problem they
+ * evaluate (NULL unbinds); sparsity pointers stay valid until the next bind. */
+int rb_casadi_bind(rb_problem* p, const double* default_vp /* [nvp] or NULL */);
+#define RB_CASADI_DECLARE(NAME)                                                          \
+  int NAME(const double** arg, double** res, long long* iw, double* w, int mem);         \
+  long long NAME##_n_in(void);                                                           \
+  long long NAME##_n_out(void);                                                          \
+  const char* NAME##_name_in(long long i);                                               \
+  const char* NAME##_name_out(long long i);                                              \
+  double NAME##_default_in(long long i);                                                 \
+  const long long* NAME##_sparsity_in(long long i);                                      \
+  const long long* NAME##_sparsity_out(long long i);                                     \
+  int NAME##_work(long long* sz_arg, long long* sz_res, long long* sz_iw, long long* sz_w); \
+  int NAME##_alloc_mem(void);                                                            \
+  int NAME##_init_mem(int mem);                                                          \
+  void NAME##_free_mem(int mem);                                                         \
+  int NAME##_checkout(void);                                                             \
+  void NAME##_release(int mem);                                                          \
+  void NAME##_incref(void);                                                              \
+  void NAME##_decref(void);
+RB_CASADI_DECLARE(nlp_f)
+RB_CASADI_DECLARE(nlp_g)
+RB_CASADI_DECLARE(nlp_grad_f)
+RB_CASADI_DECLARE(nlp_jac_g)
+RB_CASADI_DECLARE(nlp_hess_l)
+
 /* ---- KKT factor / solve of the interior-point step ---------------------------------------------
  * Replaces the sparse symmetric-indefinite solve IPOPT performs on every iteration of
  *     sol = self.solver(x0=..., lbx=..., ubx=..., lbg=..., ubg=...)   drone3d/raceline/base_raceline.py:160-165

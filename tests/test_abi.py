@@ -9,10 +9,48 @@ def test_header_symbols_exported(built_library):
     hdr = open(os.path.join(root, 'include', 'raceline_b200.h')).read()
     declared = set(re.findall(r'\b(rb_[a-z0-9_]+)\s*\(', hdr))
     assert declared, 'no declarations found'
+    # the CasADi-shaped symbols are declared through RB_CASADI_DECLARE(NAME): expand the macro
+    macro = hdr[hdr.index('#define RB_CASADI_DECLARE(NAME)'):hdr.index('RB_CASADI_DECLARE(nlp_f)')]
+    suffixes = [''] + re.findall(r'NAME##(_[a-z_]+)\(', macro)
+    names = re.findall(r'^RB_CASADI_DECLARE\((\w+)\)', hdr, re.M)
+    assert len(names) == 5 and len(suffixes) == 16
+    declared |= {n + sfx for n in names for sfx in suffixes}
     lib = load_library()
     for name in sorted(declared):
         assert hasattr(lib, name), f'{name} declared in the header but not exported'
     assert set(EXPORTS) <= declared
+
+
+def test_casadi_shaped_metadata(built_library):
+    ''' the generated-code style companions answer without a GPU: arity, names, work sizes '''
+    import ctypes
+    from aircraft_trajectory_optimization_b200.functions import load_library
+    lib = load_library()
+    want = {'nlp_f': (['x', 'p'], ['f']), 'nlp_g': (['x', 'p'], ['g']),
+            'nlp_grad_f': (['x', 'p'], ['f', 'grad_f_x']), 'nlp_jac_g': (['x', 'p'], ['g', 'jac_g_x']),
+            'nlp_hess_l': (['x', 'p', 'lam_f', 'lam_g'], ['triu_hess_gamma_x_x'])}
+    for name, (ins, outs) in want.items():
+        n_in, n_out = getattr(lib, name + '_n_in'), getattr(lib, name + '_n_out')
+        n_in.restype = n_out.restype = ctypes.c_longlong
+        assert n_in() == len(ins) and n_out() == len(outs)
+        for kind, lst in (('_name_in', ins), ('_name_out', outs)):
+            fn = getattr(lib, name + kind)
+            fn.restype, fn.argtypes = ctypes.c_char_p, [ctypes.c_longlong]
+            assert [fn(i).decode() for i in range(len(lst))] == lst
+            assert fn(len(lst)) is None
+        sz = [ctypes.c_longlong(-1) for _ in range(4)]
+        assert getattr(lib, name + '_work')(*[ctypes.byref(z) for z in sz]) == 0
+        assert [z.value for z in sz] == [len(ins), len(outs), 0, 0]
+        # nothing bound: the call fails with a message instead of touching a device
+        f = getattr(lib, name)
+        f.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int]
+        lib.rb_casadi_bind.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        assert lib.rb_casadi_bind(None, None) == 0
+        assert f(None, None, None, None, 0) != 0
+        assert b'rb_casadi_bind' in lib.rb_last_error()
+        sp = getattr(lib, name + '_sparsity_out')
+        sp.restype, sp.argtypes = ctypes.c_void_p, [ctypes.c_longlong]
+        assert sp(0) is None
 
 
 def test_product_never_imports_oracle():
