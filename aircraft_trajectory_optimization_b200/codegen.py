@@ -151,11 +151,11 @@ def rk4_cell_tables(variant: Variant):
     return J_dep, H_dep
 
 
-def _emit_fn(pf: PointFunctionGraphs, name, args, outputs, out_exprs):
+def _emit_fn(pf: PointFunctionGraphs, name, args, outputs, out_exprs, prologue=''):
     code, n_ops = pf.g.emit_c(outputs, pf.input_exprs(), out_exprs, indent='    ')
     sig = ', '.join(args)
     return (f'  // {n_ops} arithmetic instructions\n'
-            f'  __device__ __forceinline__ static void {name}({sig}) {{\n{code}\n  }}\n'), n_ops
+            f'  __device__ __forceinline__ static void {name}({sig}) {{\n{prologue}{code}\n  }}\n'), n_ops
 
 
 def generate_variant(variant: Variant, out_dir=GEN_DIR):
@@ -211,12 +211,14 @@ def generate_variant(variant: Variant, out_dir=GEN_DIR):
     # jmul / jtmul / wmul are the sparse products the direction threads run against those columns.
     code, ops['fJ_s'] = _emit_fn(pf, 'fJ_s', [cx, cfc, cvp, 'double* __restrict__ f', 'double* __restrict__ Js'],
                                  pf.f + pf.J_nodes,
-                                 [f'f[{i}]' for i in range(nz)] + [f'Js[{(i >> 1) * 2} * SCR_STRIDE + {i & 1}]' for i in range(len(pf.J))])
+                                 [f'f[{i}]' for i in range(nz)] + [f'Ja[{(i >> 1) * 2} * SCR_STRIDE + {i & 1}]' for i in range(len(pf.J))],
+                                 prologue='    double* __restrict__ Ja = static_cast<double*>(__builtin_assume_aligned(Js, 16));\n')
     parts.append(code)
     code, ops['vjpW_s'] = _emit_fn(pf, 'vjpW_s', [cx, 'const double* __restrict__ kb', cfc, cvp,
                                                   'double* __restrict__ xb', 'double* __restrict__ Ws'],
                                    pf.xb + pf.W_nodes,
-                                   [f'xb[{i}]' for i in range(nx)] + [f'Ws[{(i >> 1) * 2} * SCR_STRIDE + {i & 1}]' for i in range(len(pf.W))])
+                                   [f'xb[{i}]' for i in range(nx)] + [f'Wa[{(i >> 1) * 2} * SCR_STRIDE + {i & 1}]' for i in range(len(pf.W))],
+                                   prologue='    double* __restrict__ Wa = static_cast<double*>(__builtin_assume_aligned(Ws, 16));\n')
     parts.append(code)
 
     def sparse_product(fname, sig, lines_fn, nops, src, n_ent):

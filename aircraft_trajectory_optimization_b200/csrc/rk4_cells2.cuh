@@ -66,6 +66,9 @@ rk4_point_kernel(const RbDev d, const RbBatch b, double* __restrict__ scr) {
   constexpr int NZ = PF::NZ, NU = PF::NU, NX = PF::NX, NR = NZ + NU, CPB = SC::CPB;
   const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (cell >= (long long)b.B * d.N) return;
+  // k_1..k_3 of this thread, kept for the adjoint chain (thread-private shared-memory slots)
+  __shared__ double k_keep[3 * NZ * 128];
+  double* __restrict__ kk = k_keep + threadIdx.x;
   const int p = (int)(cell / d.N);
   const int n = (int)(cell - (long long)p * d.N);
   const double* __restrict__ w = b.x + (size_t)p * d.nw;
@@ -102,7 +105,10 @@ rk4_point_kernel(const RbDev d, const RbBatch b, double* __restrict__ scr) {
     for (int i = 0; i < NZ; ++i) {
       Sst[(SC::oK + i) * CPB] = k[i];
       Ks[i] += bw * k[i];
-      if (st < 3) xs[i] = x1[i] + an * k[i];
+      if (st < 3) {
+        kk[(st * NZ + i) * 128] = k[i];
+        xs[i] = x1[i] + an * k[i];
+      }
     }
   }
   if (!b.hess) return;
@@ -126,7 +132,7 @@ rk4_point_kernel(const RbDev d, const RbBatch b, double* __restrict__ scr) {
     for (int i = 0; i < NZ; ++i) {
       Sst[(SC::oXn + i) * CPB] = xb[i];                                  // xb_{st+1} (zero for the last stage)
       kb[i] = bw * muz[i] + an * xb[i];
-      xs[i] = x1[i] + ax * Sst[(SC::oKp + i) * CPB];
+      xs[i] = x1[i] + ax * (st > 0 ? kk[((st - 1) * NZ + i) * 128] : 0.0);
     }
     PF::vjpW_s(xs, kb, fcp, vpp, xb, Sst + SC::oW * CPB + lc);
 #pragma unroll

@@ -12,7 +12,11 @@ from aircraft_trajectory_optimization_b200.centerlines import SplineCenterlineCo
     SplineCenterline
 from aircraft_trajectory_optimization_b200 import raceline as RL
 
+# gate radii that differ from the centerline defaults (reference scripts/fig_8_cpc.py:18-19)
+TRACK_GATES = {'fig8cpc': dict(gate_ri=0.6, gate_ro=0.8)}
 TRACKS = {
+    'fig8cpc': (np.array([[0, 5, 0, -5, 0, 5, 0, -5], [0, 1, 2, 1, 0, -1, -2, -1],
+                          [10, 5, 0, -5, -10, -5, 0, 5]], dtype=float), GateShape.CIRCLE),
     'fig8': (np.array([[0, 5, 0, -5, 0, 5, 0, -5], [0, 1, 2, 1, 0, -1, -2, -1],
                        [10, 5, 0, -5, -10, -5, 0, 5]], dtype=float), GateShape.CIRCLE),
     'race': (np.array([[-1.1, 9.2, 9.2, -4.5, -4.5, 4.75, -2.8], [-1.6, 6.6, -4, -6, -6, -0.9, 6.8],
@@ -28,6 +32,8 @@ def make_line(track, cls=SplineCenterline):
     cfg = SplineCenterlineConfig(x=x.copy())
     cfg.closed = True
     cfg.gate_shape = shape
+    for k, v in TRACK_GATES.get(track, {}).items():
+        setattr(cfg, k, v)
     line = cls(cfg)
     if track == 'obs':
         line.config.gate_s = None        # scripts/obstacles.py:22-23
@@ -55,6 +61,9 @@ CASES = {
     'race_param_rk4_drone_euler': ('race', 'parametric', 'drone', True, 70, 7, False, False),
     'obs_param_colloc_drone': ('obs', 'parametric', 'drone', False, 100, 12, True, True),    # C3
     'obs_param_colloc_point': ('obs', 'parametric', 'point', False, 100, 12, True, True),    # WS of C3
+    # C4 stand-in: the reference holds no complementary-progress formulation, only its result
+    # CSV; the fig-8 track with the narrow gates of scripts/fig_8_cpc.py, parametric collocation, N = 200
+    'fig8cpc_param_colloc_drone': ('fig8cpc', 'parametric', 'drone', False, 200, 8, True, False),
 }
 
 
