@@ -79,7 +79,7 @@ cudaError_t launch_cells_t(const RbDev& d, const RbBatch& b, cudaStream_t st) {
   if (d.transcription == RB_RK4) {
     constexpr int CPB = RB_CELL_THREADS / (PF::NX + 1);
     if (!b.cell_scr) return cudaErrorInvalidValue;
-    const size_t dir_smem = (2 * (size_t)Rk4Scratch<PF>::STAGE_DOUBLES + 3 * PF::NZ * RB_CELL_THREADS) * sizeof(double);
+    const size_t dir_smem = Rk4Scratch<PF>::dir_smem_bytes(RB_CELL_THREADS);
     static bool configured_dir = false;
     if (!configured_dir) {
       cudaError_t e = cudaFuncSetAttribute(rk4_dir_kernel<PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dir_smem);

@@ -34,6 +34,14 @@ struct Rk4Scratch {
   static constexpr int SB = (oXn + NZ + 1) / 2 * 2;
   static constexpr int NS = 4 * SB;                  // doubles per cell
   static constexpr int STAGE_DOUBLES = SB * CPB;     // doubles per (group, stage) block
+  // direction kernel: per-cell staging area (doubles) [z u du | h | row multipliers (z, u rows) | row coefficients]
+  static constexpr int NU_ = PF::NU, NR_ = NZ + NU_;
+  static constexpr int cZU = 0, cH = NZ + 2 * NU_, cMU = cH + 1, cCOEF = cMU + NR_, CB = cCOEF + NR_;
+  static constexpr int NIDX = NZ + NU_ + 1;          // thread-private slot indices (Jacobian column, then Hessian column)
+  static constexpr size_t dir_smem_bytes(int threads) {
+    return (2 * (size_t)STAGE_DOUBLES + 3 * (size_t)NZ * threads + (size_t)CPB * CB) * sizeof(double) +
+           (size_t)NIDX * threads * sizeof(int);
+  }
   __host__ __device__ static size_t doubles(long long cells) { return (size_t)((cells + CPB - 1) / CPB) * NS * CPB; }
 };
 
@@ -204,8 +212,51 @@ rk4_dir_kernel(const RbDev d, const RbBatch b, const double* __restrict__ scr) {
   const int n = (int)(cell_c - (long long)p * d.N);
 
   const double* __restrict__ w = b.x + (size_t)p * d.nw;
-  const double h = w[n];
-  const double* __restrict__ zu = w + d.N + (size_t)n * (NZ + 2 * NU);
+  const size_t cr = (size_t)n * NR;
+  const double* __restrict__ lam = b.lam_g ? b.lam_g + (size_t)p * d.ng : nullptr;
+  const int lcs = live ? lc : 0;
+  // Per-cell operands every direction thread of the cell needs (z, u, du, h, row multipliers, row coefficients)
+  // are fetched once per cell by its threads together and read back from shared memory; the slot indices of
+  // this thread's Jacobian / Hessian column arrive by cp.async in thread-private shared-memory slots.  All of
+  // these global-memory latencies overlap the first TMA stage instead of stalling the sweeps one by one.
+  double* __restrict__ cellbuf = rk4_smem + 2 * SC::STAGE_DOUBLES + 3 * NZ * RB_CELL_THREADS;
+  int* __restrict__ idx = reinterpret_cast<int*>(cellbuf + CPB * SC::CB) + threadIdx.x;
+  double* __restrict__ cb = cellbuf + lcs * SC::CB;
+  if (live) {
+    const double* __restrict__ zu_g = w + d.N + (size_t)n * (NZ + 2 * NU);
+    for (int it = col; it < SC::CB; it += NV) {
+      double v;
+      if (it < SC::cH) {
+        v = zu_g[it];
+      } else if (it == SC::cH) {
+        v = w[n];
+      } else if (it < SC::cCOEF) {
+        const int c = it - SC::cMU;
+        const int r = d.cell_row[cr + c];
+        v = (r >= 0 && lam) ? lam[r] * d.cell_coef[cr + c] : 0.0;
+      } else {
+        v = d.cell_coef[cr + it - SC::cCOEF];
+      }
+      cb[it] = v;
+    }
+  }
+  auto fetch_idx = [&](int k, const int32_t* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(idx + k * RB_CELL_THREADS)),
+                 "l"(src)
+                 : "memory");
+  };
+  {
+    const int32_t* __restrict__ js0 = d.cell_jslot + (size_t)n * d.cell_nj;
+#pragma unroll
+    for (int c = 0; c < NZ; ++c) {
+      if (b.jac) fetch_idx(c, js0 + c * NV + col);
+      else idx[c * RB_CELL_THREADS] = -1;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  __syncthreads();
+  const double h = cb[SC::cH];
+  const double* __restrict__ zu = cb;                 // z, u, du of this cell
   double du[NU];
 #pragma unroll
   for (int j = 0; j < NU; ++j) du[j] = zu[NX + j];
@@ -216,17 +267,9 @@ rk4_dir_kernel(const RbDev d, const RbBatch b, const double* __restrict__ scr) {
 #pragma unroll
   for (int i = 0; i < NX; ++i) e[i] = (i == col) ? 1.0 : 0.0;
 
-  // slot indices of this thread's Jacobian column: issued now, consumed after the forward sweep
-  int jsl[NZ];
-  {
-    const int32_t* __restrict__ js0 = d.cell_jslot + (size_t)n * d.cell_nj;
-#pragma unroll
-    for (int c = 0; c < NZ; ++c) jsl[c] = b.jac ? js0[c * NV + col] : -1;
-  }
   // ---------------------------------------------------------------- forward sweep: dk_i = J_i dX_i
   // dX_i = e + a_i (h dk_{i-1} + dh k_{i-1}),  a = (0, 1/2, 1/2, 1);  dk_1..dk_3 are kept in this thread's
   // shared-memory slots for the reverse sweep
-  const int lcs = live ? lc : 0;
   const double h6 = h / 6.0, dh6 = dh / 6.0;
   double dxs[NX], dk[NZ], Ks[NZ], dKs[NZ];
 #pragma unroll
@@ -264,14 +307,9 @@ rk4_dir_kernel(const RbDev d, const RbBatch b, const double* __restrict__ scr) {
   }
 
   // ---------------------------------------------------------------- rows, multipliers
-  const size_t cr = (size_t)n * NR;
-  const double* __restrict__ lam = b.lam_g ? b.lam_g + (size_t)p * d.ng : nullptr;
   double mu[NZ];   // multiplier on out_c (already times the row coefficient)
 #pragma unroll
-  for (int c = 0; c < NZ; ++c) {
-    const int r = d.cell_row[cr + c];
-    mu[c] = (r >= 0 && lam) ? lam[r] * d.cell_coef[cr + c] : 0.0;
-  }
+  for (int c = 0; c < NZ; ++c) mu[c] = cb[SC::cMU + c];
 
   // cont(): quaternion renormalisation of zn[3:7]
   double out[NZ], dout[NZ], muz[NZ], dmuz[NZ];
@@ -316,10 +354,11 @@ rk4_dir_kernel(const RbDev d, const RbBatch b, const double* __restrict__ scr) {
     double* __restrict__ jac = b.jac ? b.jac + (size_t)p * d.nnzj : nullptr;
     const int32_t* __restrict__ js = d.cell_jslot + (size_t)n * d.cell_nj;
     if (jac) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
       for (int c = 0; c < NZ; ++c) {
-        const int s = jsl[c];
-        if (s >= 0) jac[s] = d.cell_coef[cr + c] * dout[c];
+        const int s = idx[c * RB_CELL_THREADS];
+        if (s >= 0) jac[s] = cb[SC::cCOEF + c] * dout[c];
       }
     }
     if (col < NZ) {
@@ -331,7 +370,7 @@ rk4_dir_kernel(const RbDev d, const RbBatch b, const double* __restrict__ scr) {
         double val = 0.0;
 #pragma unroll
         for (int i = 0; i < NZ; ++i) val = (i == c) ? out[i] : val;
-        val = d.cell_coef[cr + c] * val + d.cell_off[cr + c];
+        val = cb[SC::cCOEF + c] * val + d.cell_off[cr + c];
         if (pv >= 0) val += d.cell_pcoef[cr + c] * w[pv];
         if (g) g[r] = val;
         if (jac) {
@@ -344,7 +383,7 @@ rk4_dir_kernel(const RbDev d, const RbBatch b, const double* __restrict__ scr) {
       const int j = col - NZ;
       const int r = d.cell_row[cr + NZ + j];
       if (r >= 0) {
-        const double su = d.cell_coef[cr + NZ + j];
+        const double su = cb[SC::cCOEF + NZ + j];
         const double dc = d.cell_par[(size_t)n * d.cell_ncp];
         double uj = 0.0, duj = 0.0;
 #pragma unroll
@@ -395,12 +434,18 @@ rk4_dir_kernel(const RbDev d, const RbBatch b, const double* __restrict__ scr) {
 
   if (!want_h) return;
 
-  // slot indices of this thread's Hessian column: issued before the reverse sweep, consumed after it
+  // slot indices of this thread's Hessian column: issued before the reverse sweep (into the slots the Jacobian
+  // column's indices occupied), consumed after it
   const int32_t* __restrict__ hs = d.cell_hslot + (size_t)n * d.cell_nh;
-  int hsl[NX + 1];
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
-  for (int r = 0; r < NX; ++r) hsl[r] = (r <= col) ? hs[r * NL + col] : -1;
-  hsl[NX] = (col == NX) ? hs[NX * NL + NX] : -1;
+  for (int r = 0; r < NX; ++r) {
+    if (r <= col) fetch_idx(r, hs + r * NL + col);
+    else idx[r * RB_CELL_THREADS] = -1;
+  }
+  if (col == NX) fetch_idx(NX, hs + NX * NL + NX);
+  else idx[NX * RB_CELL_THREADS] = -1;
+  asm volatile("cp.async.commit_group;" ::: "memory");
   // ---------------------------------------------------------------- reverse sweep: dxb_i = W_i dX_i + J_i' dkb_i
   // kb_i = (b_i h / 6) muz + a_{i+1} h xb_{i+1};  dkb_i is its tangent;  hbar gathers a_i (dxb_i . k_{i-1} + xb_i . dk_{i-1})
   double dkb[NZ], dxb[NX];
@@ -461,25 +506,28 @@ rk4_dir_kernel(const RbDev d, const RbBatch b, const double* __restrict__ scr) {
     for (int j = 0; j < NU; ++j) gu[j] += sig * 2.0 * d.R[j] * zu[NZ + j];
   }
   // pairs (r, col) with r <= col in local order (z, u, h)
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
   for (int r = 0; r < NZ; ++r) {
-    const int s = hsl[r];
+    const int s = idx[r * RB_CELL_THREADS];
     if (s >= 0) H[s] = gz[r];
   }
 #pragma unroll
   for (int j = 0; j < NU; ++j) {
-    const int s = hsl[NZ + j];
+    const int s = idx[(NZ + j) * RB_CELL_THREADS];
     if (s >= 0) H[s] = gu[j];
   }
-  if (hsl[NX] >= 0) H[hsl[NX]] = dhb;
+  {
+    const int s = idx[NX * RB_CELL_THREADS];
+    if (s >= 0) H[s] = dhb;
+  }
   // du entries are owned by the matching u thread: (du_j, du_j) and (h, du_j)
   if (col >= NZ && col < NX) {
     const int j = col - NZ;
     double duj = 0.0;
 #pragma unroll
     for (int i = 0; i < NU; ++i) duj = (i == j) ? du[i] : duj;
-    const int r = d.cell_row[cr + NZ + j];
-    const double lu = (r >= 0 && lam) ? lam[r] * d.cell_coef[cr + NZ + j] * d.cell_par[(size_t)n * d.cell_ncp] : 0.0;
+    const double lu = cb[SC::cMU + NZ + j] * d.cell_par[(size_t)n * d.cell_ncp];
     int s = hs[(NV + j) * NL + (NV + j)];
     if (s >= 0) H[s] = sig * 2.0 * d.dR[j] * h;
     s = hs[NX * NL + (NV + j)];
