@@ -456,8 +456,8 @@ def main():
         nj, nwz = len(meta['J']), len(meta['W'])
         flop_eval = st.N * (4 * (meta['ops']['fJ_s'] + meta['ops']['vjpW_s']) + nv * 4 * (2 * nj + 2 * nwz))
         # DRAM bytes of the two shooting kernels per 128-instance chunk, from the ncu --set full capture of this
-        # command (profiles/r01_ncu_rk4_cells.txt: point 60.9 + 439.6 MB, direction 452.7 + 176.3 MB), scaled to a step
-        traffic_bytes = (60.870144e6 + 439.586560e6 + 452.706048e6 + 176.329984e6) * (B / 128.0)
+        # command (profiles/r01_ncu_rk4_cells.txt: point 32.3 + 443.6 MB, direction 453.0 + 176.8 MB), scaled to a step
+        traffic_bytes = (32.323328e6 + 443.590144e6 + 453.005056e6 + 176.750336e6) * (B / 128.0)
         roofline = dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
                         traffic=traffic_bytes, traffic_unit='bytes per step (ncu dram__bytes_read+write, profiles/r01_ncu_rk4_cells.txt)',
                         algorithmic_bytes_per_step=ab * B, peak_source=peak_src, kernel='rk4_point_kernel + rk4_dir_kernel <PF_drone_quat_param_gr> (all chunks of a step)',
