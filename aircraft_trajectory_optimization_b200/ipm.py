@@ -70,6 +70,8 @@ class IpmOptions:
     compact: bool = True               # copy the surviving instances into smaller tensors once few are left
     compact_frac: float = 0.5
     compact_min: int = 16
+    speculate: int = 2                 # spare slots of a factorisation wave try this many further delta_w candidates
+    speculate_max: int = 4             # ... up to this many when the wave is mostly empty
     window: int = 0                    # > 0: at most this many instances iterate at a time; finished ones are
                                        # replaced from the pending queue (keeps the batched kernels full)
     verbose: bool = False
@@ -89,6 +91,7 @@ class IpmResult:
     n_iter: int = 0
     n_eval: int = 0
     n_factor: int = 0
+    n_speculated: int = 0              # extra delta_w candidates factorised in spare wave slots
     t_eval: float = 0.0
     t_kkt: float = 0.0
     t_total: float = 0.0
@@ -357,40 +360,114 @@ class InteriorPoint:
             # One factorisation call per sweep (IPOPT's Algorithm IC, de-serialised over the batch): an instance
             # whose KKT matrix has the wrong inertia does not step in this sweep; it keeps its iterate, escalates
             # its own (delta_w, delta_c) and is factorised again together with everybody else in the next sweep.
-            dw_c = delta_w[:, None]
-            Ss_reg = torch.where(ineq, Ss + dw_c, torch.ones_like(Ss))
-            negd = torch.where(ineq, -1.0 / Ss_reg, torch.zeros_like(Ss)) - delta_c[:, None]
-            rhs = torch.cat([-r_x, torch.where(ineq, -c - r_s / Ss_reg, -c)], dim=1)
-            sol, st = kkt(ev['hess'], ev['jac'], Sx + dw_c, negd, rhs, active)
+            def newton(rows, dw, dc):
+                ''' (dx_diag, neg_d, rhs, Ss + dw) of the Newton system with regularisation (dw, dc); rows: index
+                tensor into the batch or None for every instance '''
+                pick = (lambda t: t) if rows is None else (lambda t: t[rows])
+                iq, Ss_, c_ = pick(ineq), pick(Ss), pick(c)
+                Ssr = torch.where(iq, Ss_ + dw[:, None], torch.ones_like(Ss_))
+                negd_ = torch.where(iq, -1.0 / Ssr, torch.zeros_like(Ss_)) - dc[:, None]
+                rhs_ = torch.cat([-pick(r_x), torch.where(iq, -c_ - pick(r_s) / Ssr, -c_)], dim=1)
+                return pick(Sx) + dw[:, None], negd_, rhs_, Ssr
+
+            def escalate(dw, ft, dwl):
+                ''' the next delta_w of Algorithm IC after a wrong-inertia factorisation with delta_w = dw '''
+                start = torch.where(dwl == 0, torch.full_like(dw, o.delta_w_first),
+                                    torch.clamp(o.kappa_w_minus * dwl, min=o.delta_w_min))
+                grow = torch.where(dwl == 0, o.kappa_w_plus_first * dw, o.kappa_w_plus * dw)
+                return torch.where(ft, start, grow)
+
+            dxd, negd, rhs, Ss_reg = newton(None, delta_w, delta_c)
+            # Speculative candidates: a launch of the factorisation kernel takes as long for one instance as for a
+            # full wave of them, so the spare slots of the last wave factorise the next `speculate` entries of
+            # some instances' delta_w escalation sequences alongside; an instance whose first matrix has the wrong
+            # inertia then picks up the first later candidate with the right one in the same sweep.  The iterates
+            # are exactly those of the one-candidate-per-sweep schedule.
+            spec_rows, spec_dw, spec_parts = None, [], []
+            wave = int(getattr(be, 'kkt_wave', 0)) if o.speculate > 0 else 0
+            if wave > 0:
+                free = (-n_act) % wave
+                # few instances in flight: every one of them gets a longer run of candidates
+                depth_s = max(o.speculate, min(o.speculate_max, free // n_act))
+                n_spec = min(free // depth_s, n_act)
+                if n_spec > 0:
+                    score = active.to(dt) * (1.0 + 2.0 * (delta_w > 0).to(dt) + (delta_w_last > 0).to(dt))
+                    spec_rows = torch.argsort(-score, stable=True)[:n_spec]
+                    dwc, ft = delta_w[spec_rows], first_try[spec_rows]
+                    for _ in range(depth_s):
+                        dwc = escalate(dwc, ft, delta_w_last[spec_rows])
+                        ft = torch.zeros_like(ft)
+                        spec_dw.append(dwc)
+                        spec_parts.append(newton(spec_rows, dwc, delta_c[spec_rows]))
+            if spec_rows is None:
+                sol, st = kkt(ev['hess'], ev['jac'], dxd, negd, rhs, active)
+            else:
+                t0 = time.perf_counter()
+                idx_act = torch.nonzero(active).squeeze(1)
+                idx_all = torch.cat([idx_act] + [spec_rows] * len(spec_parts))
+                cat = lambda k, full: torch.cat([full[idx_act]] + [p_[k] for p_ in spec_parts])
+                sol_all, st_all = be.kkt_solve_rows(ev['hess'], ev['jac'], idx_all, cat(0, dxd), cat(1, negd), cat(2, rhs),
+                                                    o.refine_steps)
+                if dev.type == 'cuda':
+                    torch.cuda.synchronize(dev)
+                res.t_kkt += time.perf_counter() - t0
+                res.n_factor += 1
+                res.n_speculated += int(spec_rows.numel()) * len(spec_parts)
+                na = int(idx_act.numel())
+                sol = torch.zeros(B, n + m, dtype=dt, device=dev)
+                st = torch.zeros(B, 2, dtype=st_all.dtype, device=dev)
+                st[:, 1] = m
+                sol.index_copy_(0, idx_act, sol_all[:na])
+                st.index_copy_(0, idx_act, st_all[:na])
+                spec_pos = torch.full((B,), -1, dtype=torch.long, device=dev)
+                spec_pos[spec_rows] = torch.arange(spec_rows.numel(), device=dev)
             n_fact = n_fact + active.long()
             if o.verbose:
                 print(f'        dw={float(delta_w[0]):.2e} dc={float(delta_c[0]):.2e} bad_piv={int(st[0, 0])} '
                       f'neg={int(st[0, 1])} (want {m}) attempt {int(attempts[0])}')
-            finite = torch.isfinite(sol).all(1)
-            singular = (st[:, 0] != 0) | ~finite
-            wrong_inertia = st[:, 1] != m
-            bad = active & (singular | wrong_inertia)
-            moved = active & ~bad
+            pending = active.clone()                 # instances whose current candidate is still to be judged
+            bad = torch.zeros_like(active)
+            moved = torch.zeros_like(active)
+            for depth in range(len(spec_parts) + 1):
+                finite = torch.isfinite(sol).all(1)
+                singular = (st[:, 0] != 0) | ~finite
+                wrong_inertia = st[:, 1] != m
+                bad_j = pending & (singular | wrong_inertia)
+                ok_j = pending & ~bad_j
+                moved = moved | ok_j
+                delta_w_last = torch.where(ok_j & (delta_w > 0), delta_w, delta_w_last)
+                # too few negative eigenvalues or a vanishing pivot: the constraint Jacobian is (numerically) rank
+                # deficient -> perturb the constraint block first and retry with the same delta_w
+                degenerate = bad_j & (singular | (st[:, 1] < m)) & (delta_c == 0)
+                esc = bad_j & ~degenerate
+                delta_w_next = torch.where(esc, escalate(delta_w, first_try, delta_w_last), delta_w)
+                delta_c_next = torch.where(degenerate, o.delta_c_bar * mu ** o.kappa_c, delta_c)
+                attempts = torch.where(bad_j, attempts + 1, torch.where(ok_j, torch.zeros_like(attempts), attempts))
+                status[bad_j & ((delta_w_next > o.delta_w_max) | (attempts > 60))] = 3
+                # instances that step start their next iteration from delta_w = delta_c = 0 again
+                delta_w = torch.where(bad_j, delta_w_next, torch.where(ok_j, torch.zeros_like(delta_w), delta_w))
+                delta_c = torch.where(bad_j, delta_c_next, torch.where(ok_j, torch.zeros_like(delta_c), delta_c))
+                first_try = torch.where(bad_j, first_try & ~esc, torch.where(ok_j, torch.ones_like(first_try), first_try))
+                take = torch.zeros_like(active)
+                if depth < len(spec_parts):
+                    # the candidate factorised alongside is this instance's next attempt
+                    cand_dw = torch.zeros_like(delta_w)
+                    cand_dw[spec_rows] = spec_dw[depth]
+                    take = esc & (status == -1) & (spec_pos >= 0) & (cand_dw == delta_w)
+                bad = bad | (bad_j & ~take)
+                if not bool(take.any()):
+                    break
+                rows_t = torch.nonzero(take).squeeze(1)
+                src = na + depth * int(spec_rows.numel()) + spec_pos[rows_t]
+                sol.index_copy_(0, rows_t, sol_all[src])
+                st.index_copy_(0, rows_t, st_all[src])
+                Ss_reg.index_copy_(0, rows_t, spec_parts[depth][3][spec_pos[rows_t]])
+                n_fact = n_fact + take.long()
+                pending = take
             mv = moved[:, None]
             dx = torch.where(mv, sol[:, :n], torch.zeros_like(x))
             dy = torch.where(mv, sol[:, n:], torch.zeros_like(y))
             ds = torch.where(mv & ineq, (dy - r_s) / Ss_reg, torch.zeros_like(s))
-            delta_w_last = torch.where(moved & (delta_w > 0), delta_w, delta_w_last)
-            # too few negative eigenvalues or a vanishing pivot: the constraint Jacobian is (numerically) rank
-            # deficient -> perturb the constraint block first and retry with the same delta_w
-            degenerate = bad & (singular | (st[:, 1] < m)) & (delta_c == 0)
-            esc = bad & ~degenerate
-            start = torch.where(delta_w_last == 0, torch.full_like(delta_w, o.delta_w_first),
-                                torch.clamp(o.kappa_w_minus * delta_w_last, min=o.delta_w_min))
-            grow = torch.where(delta_w_last == 0, o.kappa_w_plus_first * delta_w, o.kappa_w_plus * delta_w)
-            delta_w_next = torch.where(esc, torch.where(first_try, start, grow), delta_w)
-            delta_c_next = torch.where(degenerate, o.delta_c_bar * mu ** o.kappa_c, delta_c)
-            attempts = torch.where(bad, attempts + 1, torch.zeros_like(attempts))
-            status[bad & ((delta_w_next > o.delta_w_max) | (attempts > 60))] = 3
-            # instances that step start their next iteration from delta_w = delta_c = 0 again
-            delta_w = torch.where(bad, delta_w_next, torch.zeros_like(delta_w))
-            delta_c = torch.where(bad, delta_c_next, torch.zeros_like(delta_c))
-            first_try = torch.where(bad, first_try & ~esc, torch.ones_like(first_try))
             stalled = bad & (status == -1)
 
             dzL = (mu_c * iL - zL - zL * iL * dx) * fL
@@ -543,7 +620,7 @@ class CudaBackend:
         self.vp = vp                                   # device tensor (nvp,) or (B, nvp)
         self._vp_full = vp
         self.K = kkt_solver or KktSolver(self.st)
-        self.refine_tol = 1e-10
+        self.refine_tol = 1e-13
         self._buf = {}
 
     def _out(self, name, shape, dev):
@@ -612,20 +689,37 @@ class CudaBackend:
     def kkt_matvec(self, hess, jac, dx_diag, neg_d, vec):
         return self.K.matvec(hess, jac, dx_diag.contiguous(), neg_d.contiguous(), vec.contiguous())
 
-    def kkt_solve(self, hess, jac, dx_diag, neg_d, rhs, refine_steps, idx=None):
-        B = rhs.shape[0]
-        if idx is not None:
-            hess, jac, dx_diag, neg_d, rhs = hess[idx], jac[idx], dx_diag[idx], neg_d[idx], rhs[idx]
+    @property
+    def kkt_wave(self):
+        ''' instances one launch of the factorisation kernel holds at once (CTAs per SM x SMs): a launch with fewer
+        instances takes as long, so the driver fills the spare slots with speculative regularisation candidates '''
+        sms = torch.cuda.get_device_properties(self.vp.device).multi_processor_count
+        return sms * (3 if self.K.ks.bmax <= 64 else 1)
+
+    def kkt_solve_rows(self, hess, jac, idx, dx_diag, neg_d, rhs, refine_steps):
+        ''' rows `idx` of hess / jac (repeats allowed) with dx_diag / neg_d / rhs given row by row '''
+        return self._kkt_core(hess[idx], jac[idx], dx_diag, neg_d, rhs, refine_steps)
+
+    def _kkt_core(self, hess, jac, dx_diag, neg_d, rhs, refine_steps):
         dx_diag, neg_d, rhs = dx_diag.contiguous(), neg_d.contiguous(), rhs.contiguous()
         sol, status = self.K.factor_solve(hess, jac, dx_diag, neg_d, rhs)
         sol = sol.clone()
         scale = torch.clamp(rhs.abs().amax(1), min=1.0)
         for _ in range(refine_steps):
             r = rhs - self.K.matvec(hess, jac, dx_diag, neg_d, sol)
-            # iterative refinement only while some instance is above the fp64 noise floor of its right-hand side
-            if not bool(((r.abs().amax(1) / scale) > self.refine_tol).any()):
+            # iterative refinement only while some instance is above the fp64 noise floor of its right-hand side;
+            # the correction is applied instance by instance, so a result does not depend on the rest of the batch
+            need = (r.abs().amax(1) / scale) > self.refine_tol
+            if not bool(need.any()):
                 break
-            sol = sol + self.K.resolve(hess, jac, dx_diag, neg_d, r)
+            sol = torch.where(need[:, None], sol + self.K.resolve(hess, jac, dx_diag, neg_d, r), sol)
+        return sol, status
+
+    def kkt_solve(self, hess, jac, dx_diag, neg_d, rhs, refine_steps, idx=None):
+        B = rhs.shape[0]
+        if idx is not None:
+            hess, jac, dx_diag, neg_d, rhs = hess[idx], jac[idx], dx_diag[idx], neg_d[idx], rhs[idx]
+        sol, status = self._kkt_core(hess, jac, dx_diag, neg_d, rhs, refine_steps)
         if idx is None:
             return sol, status
         sol_f = torch.zeros(B, sol.shape[1], dtype=sol.dtype, device=sol.device)

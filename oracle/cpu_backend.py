@@ -57,6 +57,12 @@ class OracleBackend:
             out[b] = K @ vec[b].numpy()
         return torch.from_numpy(out)
 
+    kkt_wave = 0       # instances per kernel wave (0: no speculative candidates); tests set it
+
+    def kkt_solve_rows(self, hess, jac, idx, dx_diag, neg_d, rhs, refine_steps):
+        ''' rows `idx` of hess / jac (repeats allowed) with dx_diag / neg_d / rhs given row by row '''
+        return self.kkt_solve(hess[idx], jac[idx], dx_diag, neg_d, rhs, refine_steps)
+
     def kkt_solve(self, hess, jac, dx_diag, neg_d, rhs, refine_steps, idx=None):
         B = rhs.shape[0]
         sol = np.zeros(rhs.shape)

@@ -75,3 +75,32 @@ def test_drone_warm_start_chain(built_library):
     q = np.array([s.q.to_vec() for s in res.states[1:]]) if hasattr(res.states[0], 'q') else None
     if q is not None:
         assert np.abs(np.linalg.norm(q, axis=1) - 1).max() < 1e-6
+
+
+@pytest.mark.gpu
+def test_speculative_candidates_and_batch_composition_do_not_change_results(built_library):
+    ''' the spare slots of a factorisation wave try further delta_w candidates: same iterates, fewer sweeps; and an
+    instance's answer does not depend on which other instances share its batch '''
+    from aircraft_trajectory_optimization_b200.ipm import IpmOptions
+    prod = build_product('race_global_rk4_point', N=7)
+    st = prod.structure
+    prod.solver.verbose = False
+    rng = np.random.default_rng(1)
+    X0 = np.tile(st.w0, (3, 1))
+    X0[1] += 0.05 * rng.standard_normal(st.nw)
+    X0[2] += 0.10 * rng.standard_normal(st.nw)
+    kw = dict(lbx=st.lbw, ubx=st.ubw, lbg=st.lbg, ubg=st.ubg)
+    prod.solver.options = IpmOptions(speculate=0)
+    base = prod.solver(x0=X0, **kw)
+    r0 = prod.solver.result
+    assert r0.n_speculated == 0 and (r0.factorisations_each > r0.iterations.cpu().numpy()).any()
+    prod.solver.options = IpmOptions(speculate=2)
+    spec = prod.solver(x0=X0, **kw)
+    r1 = prod.solver.result
+    assert r1.n_speculated > 0 and r1.n_factor < r0.n_factor
+    assert np.array_equal(r0.factorisations_each, r1.factorisations_each)
+    for k in ('x', 'lam_g', 'lam_x'):
+        assert np.array_equal(base[k], spec[k]), k
+    # the hardest start alone gives the same answer as inside the batch
+    alone = prod.solver(x0=X0[2], **kw)
+    assert np.array_equal(alone['x'], spec['x'][2])

@@ -85,3 +85,32 @@ def test_compaction_and_window_do_not_change_results():
     assert base.success.all() and len(set(base.iterations.tolist())) > 1      # they finish at different times
     assert torch.equal(base.status, comp.status) and torch.equal(base.iterations, comp.iterations)
     assert torch.equal(base.x, comp.x) and torch.equal(base.lam_g, comp.lam_g) and torch.equal(base.lam_x, comp.lam_x)
+
+
+def test_speculative_regularisation_candidates_do_not_change_results():
+    ''' spare slots of a factorisation wave try the next delta_w candidates: fewer sweeps, identical iterates '''
+    from oracle.nlp_functions import OracleNLP
+    from oracle.cpu_backend import OracleBackend
+    from aircraft_trajectory_optimization_b200.ipm import InteriorPoint, IpmOptions
+    from aircraft_trajectory_optimization_b200.kkt import build_kkt_structure
+    prod, ref = build_case('race_global_rk4_point', N=7)
+    st = prod.structure
+    nlp = OracleNLP(ref)
+    T = lambda a: torch.from_numpy(np.asarray(a, dtype=float))
+    rng = np.random.default_rng(1)
+    X0 = np.tile(st.w0, (3, 1))
+    X0[1] += 0.05 * rng.standard_normal(st.nw)
+    X0[2] += 0.10 * rng.standard_normal(st.nw)
+    args = (T(X0), T(st.lbw), T(st.ubw), T(st.lbg), T(st.ubg))
+    be = OracleBackend(nlp, nlp, ks=build_kkt_structure(st))
+    base = InteriorPoint(be, IpmOptions(max_iter=150, speculate=0)).solve(*args)
+    assert base.n_speculated == 0
+    # the delta_w escalation is exercised: some instance needed more factorisations than iterations
+    assert (base.factorisations_each > base.iterations.numpy()).any()
+    be.kkt_wave = 8                       # 3 instances in flight: 5 spare slots -> 2 instances x 2 candidates
+    spec = InteriorPoint(be, IpmOptions(max_iter=150, speculate=2)).solve(*args)
+    be.kkt_wave = 0
+    assert spec.n_speculated > 0 and spec.n_factor < base.n_factor
+    assert torch.equal(base.status, spec.status) and torch.equal(base.iterations, spec.iterations)
+    assert np.array_equal(base.factorisations_each, spec.factorisations_each)
+    assert torch.equal(base.x, spec.x) and torch.equal(base.lam_g, spec.lam_g) and torch.equal(base.lam_x, spec.lam_x)
