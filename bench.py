@@ -267,6 +267,8 @@ def run_solves(args, dev, rank, world, dist):
                lap_time_nominal=float(laps[0]), lap_time_min=float(laps[okf].min()) if okf.any() else None,
                lap_time_max=float(laps[okf].max()) if okf.any() else None,
                warm_start_setup_s=t_build, gpu_launches=int(prod.functions.launch_count() - lib_launch0),
+               speculative_factorisations=int(prod.solver.result.n_speculated),
+               return_status_rank0={str(k): int(v) for k, v in zip(*np.unique(np.asarray(s['return_status']), return_counts=True))},
                workload='C5 shape: C2 x multi-start (w0_ws + 0.05*scale*N(0,1)) x vehicle parameters U[0.9,1.1]; '
                         'instance 0 of rank 0 is the nominal race.py problem')
     if rank == 0 and not args.no_cpu:
