@@ -232,7 +232,7 @@ def run_solves(args, dev, rank, world, dist):
     prod.solver.verbose = False
     prod.solver.max_iter = args.solves_max_iter
     from aircraft_trajectory_optimization_b200.ipm import IpmOptions
-    prod.solver.options = IpmOptions(window=args.solves_window)
+    prod.solver.options = IpmOptions(window=args.solves_window, refine_steps=args.solves_refine)
     lib_launch0 = prod.functions.launch_count()
     torch.cuda.synchronize(dev)
     if world > 1:
@@ -321,6 +321,7 @@ def main():
     ap.add_argument('--no-solves', action='store_true', help='skip the converged-solves leg')
     ap.add_argument('--solves-batch', type=int, default=2048, help='multi-start instances per GPU in the solves leg')
     ap.add_argument('--solves-window', type=int, default=888, help='instances iterating at a time (continuous batching)')
+    ap.add_argument('--solves-refine', type=int, default=2, help='iterative-refinement steps per KKT solve')
     ap.add_argument('--solves-max-iter', type=int, default=300,
                     help='iteration cap per instance in the multi-start sweep (p99 of converged instances is ~280; '
                          'the reference sets 1000 for its single solves)')
