@@ -667,10 +667,11 @@ kkt_resolve_kernel(const RbKktDev d, const RbKktBatch bt) {
 // of the next block are fetched by TMA bulk copies (cp.async.bulk + mbarrier, double-buffered) while the current
 // block is applied, so the sequential walk over the chain is not exposed to global-memory latency; eight threads
 // share every row of the matrix-vector products.
+#define RB_KKT_RBUF 3   // factor blocks in flight per CTA in the re-solve (TMA pipeline depth)
 __global__ void __launch_bounds__(RB_KKT_THREADS)
 kkt_resolve_tma_kernel(const RbKktDev d, const RbKktBatch bt) {
   extern __shared__ __align__(128) double kkt_smem[];
-  __shared__ __align__(8) unsigned long long bars[2];
+  __shared__ __align__(8) unsigned long long bars[RB_KKT_RBUF];
   const int p = blockIdx.x;
   if (p >= bt.B) return;
   const int tid = threadIdx.x;
@@ -679,7 +680,7 @@ kkt_resolve_tma_kernel(const RbKktDev d, const RbKktBatch bt) {
   const int SZ_S = bmax * d.ldS, SZ_Y = bmax * d.ldY;                // doubles per block of the two factor arrays (even)
   const int BUF = SZ_S + SZ_Y;
   double* buf0 = kkt_smem;
-  double* y = kkt_smem + 2 * BUF;     // [nbb] current block rhs
+  double* y = kkt_smem + RB_KKT_RBUF * BUF;     // [nbb] current block rhs
   double* xn = y + nbb;               // [nbb] solution of the block above (backward)
   double* rc = xn + nbb;              // [mmax] carry
   double* xb = rc + mmax;             // [nb]
@@ -693,8 +694,8 @@ kkt_resolve_tma_kernel(const RbKktDev d, const RbKktBatch bt) {
   double* __restrict__ Xr = bt.Xr + (size_t)p * N * bmax;
 
   auto issue = [&](int step, int n, bool with_s) {
-    const unsigned bar = (unsigned)__cvta_generic_to_shared(&bars[step & 1]);
-    double* dstS = buf0 + (size_t)(step & 1) * BUF;
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&bars[step % RB_KKT_RBUF]);
+    double* dstS = buf0 + (size_t)(step % RB_KKT_RBUF) * BUF;
     const unsigned bytes = (unsigned)((with_s ? SZ_S : 0) + SZ_Y) * 8u;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
     if (with_s)
@@ -708,8 +709,8 @@ kkt_resolve_tma_kernel(const RbKktDev d, const RbKktBatch bt) {
                  : "memory");
   };
   auto wait = [&](int step) {
-    const unsigned bar = (unsigned)__cvta_generic_to_shared(&bars[step & 1]);
-    const unsigned parity = (step >> 1) & 1;
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&bars[step % RB_KKT_RBUF]);
+    const unsigned parity = (step / RB_KKT_RBUF) & 1;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -723,8 +724,8 @@ kkt_resolve_tma_kernel(const RbKktDev d, const RbKktBatch bt) {
         : "memory");
   };
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&bars[0])));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&bars[1])));
+    for (int i = 0; i < RB_KKT_RBUF; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&bars[i])));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -732,23 +733,28 @@ kkt_resolve_tma_kernel(const RbKktDev d, const RbKktBatch bt) {
   const int nsteps = 2 * N - 1;
   auto block_of = [&](int step) { return step < N ? step : 2 * N - 2 - step; };
   if (tid == 0) {
-    issue(0, block_of(0), true);
-    if (nsteps > 1) issue(1, block_of(1), 1 < N);
+    for (int s0 = 0; s0 < RB_KKT_RBUF && s0 < nsteps; ++s0) issue(s0, block_of(s0), s0 < N);
   }
   const int grp = tid >> 3, part = tid & 7;          // eight threads per row of a product
   int m_prev = 0;
   const int32_t* cr_prev = nullptr;
+  // the right-hand-side entries of the next block are gathered one step ahead (blocks have at most 64 unknowns)
+  double y_next = (tid < d.blk_ptr[1] - d.blk_ptr[0]) ? rhs[d.unk[d.blk_ptr[0] + tid]] : 0.0;
   for (int n = 0; n < N; ++n) {
     const int step = n;
     const int u0 = d.blk_ptr[n], b = d.blk_ptr[n + 1] - u0;
-    for (int i = tid; i < b; i += blockDim.x) y[i] = rhs[d.unk[u0 + i]];
+    if (tid < b) y[tid] = y_next;
     __syncthreads();
+    if (n + 1 < N) {
+      const int u1 = d.blk_ptr[n + 1], b1 = d.blk_ptr[n + 2] - u1;
+      if (tid < b1) y_next = rhs[d.unk[u1 + tid]];
+    }
     if (n > 0) {
       for (int a = tid; a < m_prev; a += blockDim.x) y[cr_prev[a]] -= rc[a];
       __syncthreads();
     }
     wait(step);
-    const double* __restrict__ Sn = buf0 + (size_t)(step & 1) * BUF;
+    const double* __restrict__ Sn = buf0 + (size_t)(step % RB_KKT_RBUF) * BUF;
     const double* __restrict__ Yn = Sn + SZ_S;
     // (loop bounds are uniform over the block: every lane takes part in the shuffles)
     for (int ib = 0; ib < b; ib += RB_KKT_THREADS / 8) {
@@ -778,33 +784,37 @@ kkt_resolve_tma_kernel(const RbKktDev d, const RbKktBatch bt) {
       cr_prev = d.cr + d.cr_ptr[n];
     }
     __syncthreads();                                   // this buffer and y are free again
-    if (tid == 0 && step + 2 < nsteps) issue(step + 2, block_of(step + 2), step + 2 < N);
+    if (tid == 0 && step + RB_KKT_RBUF < nsteps) issue(step + RB_KKT_RBUF, block_of(step + RB_KKT_RBUF), step + RB_KKT_RBUF < N);
   }
   {
     const int b = d.blk_ptr[N] - d.blk_ptr[N - 1];
     for (int i = tid; i < b; i += blockDim.x) xn[i] = Xr[(size_t)(N - 1) * bmax + i];
     __syncthreads();
   }
+  // z_n of the next block down is read one step ahead
+  double z_next = (N >= 2 && tid < d.blk_ptr[N - 1] - d.blk_ptr[N - 2]) ? Xr[(size_t)(N - 2) * bmax + tid] : 0.0;
   for (int n = N - 2; n >= 0; --n) {
     const int step = 2 * N - 2 - n;
     const int b = d.blk_ptr[n + 1] - d.blk_ptr[n];
+    const double z_cur = z_next;
+    if (n > 0 && tid < d.blk_ptr[n] - d.blk_ptr[n - 1]) z_next = Xr[(size_t)(n - 1) * bmax + tid];
     const int m = d.cr_ptr[n + 1] - d.cr_ptr[n];
     const int32_t* __restrict__ cr = d.cr + d.cr_ptr[n];
     for (int a = tid; a < m; a += blockDim.x) rc[a] = xn[cr[a]];
     wait(step);
     __syncthreads();
-    const double* __restrict__ Yn = buf0 + (size_t)(step & 1) * BUF + SZ_S;
-    for (int i = tid; i < b; i += blockDim.x) {
-      double acc = Xr[(size_t)n * bmax + i];
-      for (int a = 0; a < m; ++a) acc -= Yn[i * d.ldY + a] * rc[a];
-      y[i] = acc;
+    const double* __restrict__ Yn = buf0 + (size_t)(step % RB_KKT_RBUF) * BUF + SZ_S;
+    if (tid < b) {
+      double acc = z_cur;
+      for (int a = 0; a < m; ++a) acc -= Yn[tid * d.ldY + a] * rc[a];
+      y[tid] = acc;
     }
     __syncthreads();
     for (int i = tid; i < b; i += blockDim.x) {
       xn[i] = y[i];
       Xr[(size_t)n * bmax + i] = y[i];
     }
-    if (tid == 0 && step + 2 < nsteps) issue(step + 2, block_of(step + 2), false);
+    if (tid == 0 && step + RB_KKT_RBUF < nsteps) issue(step + RB_KKT_RBUF, block_of(step + RB_KKT_RBUF), false);
     __syncthreads();
   }
   if (nb > 0) {

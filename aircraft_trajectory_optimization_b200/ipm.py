@@ -66,7 +66,8 @@ class IpmOptions:
     kappa_w_plus_first: float = 100.0
     delta_c_bar: float = 1e-8
     kappa_c: float = 0.25
-    refine_steps: int = 2
+    refine_steps: int = 1               # IPOPT min_refinement_steps; further steps change neither the iteration counts nor
+                                       # the converged fraction of the C5 batch, each costs ~8 ms per 444-instance wave
     compact: bool = True               # copy the surviving instances into smaller tensors once few are left
     compact_frac: float = 0.5
     compact_min: int = 16

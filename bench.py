@@ -321,7 +321,7 @@ def main():
     ap.add_argument('--no-solves', action='store_true', help='skip the converged-solves leg')
     ap.add_argument('--solves-batch', type=int, default=2048, help='multi-start instances per GPU in the solves leg')
     ap.add_argument('--solves-window', type=int, default=888, help='instances iterating at a time (continuous batching)')
-    ap.add_argument('--solves-refine', type=int, default=2, help='iterative-refinement steps per KKT solve')
+    ap.add_argument('--solves-refine', type=int, default=1, help='iterative-refinement steps per KKT solve')
     ap.add_argument('--solves-max-iter', type=int, default=300,
                     help='iteration cap per instance in the multi-start sweep (p99 of converged instances is ~280; '
                          'the reference sets 1000 for its single solves)')
