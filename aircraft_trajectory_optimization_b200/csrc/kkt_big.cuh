@@ -13,32 +13,38 @@
 
 #define RB_KKTB_THREADS 1024
 
+#define RB_KKTB_GRP 8      // Gauss-Jordan update vectors accumulated before one pass over the block applies them
+
 struct KktBigSmem {
-  double *c1, *r1, *c2, *r2, *dg, *Lc, *carry, *rcarry, *xb;
+  double *Cg, *Rg;          // [RB_KKTB_GRP][nbb] update vectors of the current group
+  double *rowA, *rowB;      // current rows k and r of the block (pivot choice, then the pivot rows)
+  double *dg, *Lc, *carry, *rcarry, *xb;
   int* swept;
-  int* piv;   // type, p, q
+  int* ingrp;               // index pivoted inside the current group
+  int* piv;                 // type, p, q, buffer of row p, k
 };
 
 __host__ __device__ inline size_t kktb_smem_bytes(int bmax, int nb, int mmax, int qmax) {
   const size_t nbb = nb > bmax ? nb : bmax, nrhs = 1 + nb;
-  const size_t dbl = 6 * nbb + (size_t)mmax * qmax + (size_t)mmax * mmax + (size_t)mmax * nrhs;
-  return dbl * sizeof(double) + (nbb + 8) * sizeof(int);
+  const size_t dbl = (2 * RB_KKTB_GRP + 4) * nbb + (size_t)mmax * qmax + (size_t)mmax * mmax + (size_t)mmax * nrhs;
+  return dbl * sizeof(double) + (2 * nbb + 8) * sizeof(int);
 }
 
 __device__ inline KktBigSmem kktb_carve(double* s, int bmax, int nb, int mmax, int qmax) {
   const size_t nbb = nb > bmax ? nb : bmax, nrhs = 1 + nb;
   KktBigSmem k;
-  k.c1 = s; s += nbb;
-  k.r1 = s; s += nbb;
-  k.c2 = s; s += nbb;
-  k.r2 = s; s += nbb;
+  k.Cg = s; s += RB_KKTB_GRP * nbb;
+  k.Rg = s; s += RB_KKTB_GRP * nbb;
+  k.rowA = s; s += nbb;
+  k.rowB = s; s += nbb;
   k.dg = s; s += nbb;
   k.xb = s; s += nbb;
   k.Lc = s; s += (size_t)mmax * qmax;
   k.carry = s; s += (size_t)mmax * mmax;
   k.rcarry = s; s += (size_t)mmax * nrhs;
   k.swept = reinterpret_cast<int*>(s);
-  k.piv = k.swept + nbb;
+  k.ingrp = k.swept + nbb;
+  k.piv = k.ingrp + nbb;
   return k;
 }
 
@@ -48,18 +54,73 @@ __host__ __device__ inline size_t kktb_work_doubles(int bmax, int nb, int mmax) 
   return 2 * nbb * nrhs + (size_t)bmax * mmax + nbb * nbb;
 }
 
-// in-place inverse of the symmetric b x b matrix M (global memory, row-major, leading dimension LD)
-__device__ int kktb_sym_invert(double* __restrict__ M, int LD, int b, const KktBigSmem& s, int* neg) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
+// In-place inverse of the symmetric b x b matrix M (global memory, row-major, leading dimension LD) by
+// Gauss-Jordan steps with Bunch-Kaufman pivoting, the updates applied in groups.
+//
+// A step on pivot p maps M to Z_p(M) - c r' where Z_p zeroes row and column p, c_i = a_ip (c_p = -1),
+// r_j = a_pj / a_pp (r_p = 1 / a_pp); a 2x2 step on (p, q) subtracts two such terms.  After the steps s = 1..g of a
+// group the block is  Z_P(M) - sum_s c~_s r~_s'  where P is the set of the group's pivots and c~_s, r~_s are
+// c_s, r_s with the entries of the LATER pivots of the group zeroed.  The block itself (0.8 MB, L2-resident) is
+// therefore read and written once per group of RB_KKTB_GRP vectors instead of once per pivot; in between, warp 0
+// reconstructs the one or two current rows the pivot choice needs from the stored block and the group's
+// vectors, and the current diagonal is carried in shared memory.  Pivot columns come from pivot rows: the
+// partially inverted matrix satisfies M[j][p] = -M[p][j] for swept j and M[j][p] = M[p][j] otherwise.
+__device__ int kktb_sym_invert(double* __restrict__ M, int LD, int b, const KktBigSmem& s, int* neg, int nbb) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
   const double alpha = 0.6403882032022076;
   int bad = 0, nneg = 0;
   for (int i = tid; i < b; i += nthreads) {
     s.swept[i] = 0;
+    s.ingrp[i] = 0;
     s.dg[i] = M[(size_t)i * LD + i];
   }
   __syncthreads();
-  int remaining = b;
+  int remaining = b, ng = 0;        // ng: vectors in the current group (uniform over the CTA)
+
+  // current row i of the block -> buf (every thread one or more entries)
+  auto current_row = [&](int i, double* __restrict__ buf) {
+    const bool gi = s.ingrp[i] != 0;
+    for (int j = tid; j < b; j += nthreads) {
+      double v = (gi || s.ingrp[j]) ? 0.0 : M[(size_t)i * LD + j];
+      for (int t = 0; t < ng; ++t) v -= s.Cg[t * nbb + i] * s.Rg[t * nbb + j];
+      buf[j] = v;
+    }
+  };
+  // M <- Z_P(M) - sum_t C_t R_t' : two rows per warp pass, the C entries of the rows in registers
+  auto flush = [&]() {
+    for (int i0 = 2 * warp; i0 < b; i0 += 2 * nwarps) {
+      const int i1 = (i0 + 1 < b) ? i0 + 1 : i0;
+      double c0[RB_KKTB_GRP], c1[RB_KKTB_GRP];
+#pragma unroll
+      for (int t = 0; t < RB_KKTB_GRP; ++t) {
+        c0[t] = t < ng ? s.Cg[t * nbb + i0] : 0.0;
+        c1[t] = t < ng ? s.Cg[t * nbb + i1] : 0.0;
+      }
+      const bool g0 = s.ingrp[i0] != 0, g1 = s.ingrp[i1] != 0;
+      double* __restrict__ row0 = M + (size_t)i0 * LD;
+      double* __restrict__ row1 = M + (size_t)i1 * LD;
+      for (int j = lane; j < b; j += 32) {
+        const bool gj = s.ingrp[j] != 0;
+        double v0 = (g0 || gj) ? 0.0 : row0[j];
+        double v1 = (g1 || gj) ? 0.0 : row1[j];
+#pragma unroll
+        for (int t = 0; t < RB_KKTB_GRP; ++t) {
+          const double rj = t < ng ? s.Rg[t * nbb + j] : 0.0;
+          v0 -= c0[t] * rj;
+          v1 -= c1[t] * rj;
+        }
+        row0[j] = v0;
+        if (i1 != i0) row1[j] = v1;
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < b; i += nthreads) s.ingrp[i] = 0;
+    ng = 0;
+    __syncthreads();
+  };
+
   while (remaining > 0) {
+    // ---- pivot choice: warp 0 scans, every thread helps to reconstruct the one or two current rows it needs
     if (warp == 0) {
       // k: largest remaining diagonal entry
       float v = -1.f;
@@ -74,15 +135,21 @@ __device__ int kktb_sym_invert(double* __restrict__ M, int LD, int b, const KktB
         }
       int kk;
       kkt_argmax32(v, k, kk);
-      k = kk;
-      int type = 1, p = k, q = k;
+      if (lane == 0) s.piv[4] = kk;
+    }
+    __syncthreads();
+    const int k = s.piv[4];
+    current_row(k, s.rowA);
+    __syncthreads();
+    if (warp == 0) {
+      int type = 1, p = k, q = k, r = k, need_r = 0;
       if (remaining > 1) {
         // lambda = largest remaining off-diagonal entry of row k (= column k by symmetry of the unswept part)
-        v = -1.f;
-        int r = 0x7fffffff;
+        float v = -1.f;
+        r = 0x7fffffff;
         for (int j = lane; j < b; j += 32)
           if (!s.swept[j] && j != k) {
-            const float a = kkt_mag(M[(size_t)k * LD + j]);
+            const float a = kkt_mag(s.rowA[j]);
             if (a > v) {
               v = a;
               r = j;
@@ -91,40 +158,57 @@ __device__ int kktb_sym_invert(double* __restrict__ M, int LD, int b, const KktB
         int rr;
         kkt_argmax32(v, r, rr);
         r = rr;
-        const double akk = fabs(s.dg[k]), lam = fabs(M[(size_t)k * LD + r]);
-        if (!(akk >= alpha * lam)) {
-          v = -1.f;
-          int t = 0x7fffffff;
-          for (int j = lane; j < b; j += 32)
-            if (!s.swept[j] && j != r) {
-              const float a = kkt_mag(M[(size_t)r * LD + j]);
-              if (a > v) {
-                v = a;
-                t = j;
-              }
-            }
-          int tt;
-          kkt_argmax32(v, t, tt);
-          const double sig = fabs(M[(size_t)r * LD + tt]);
-          if (akk * sig >= alpha * lam * lam) {
-            p = k;
-          } else if (fabs(s.dg[r]) >= alpha * sig) {
-            p = r;
-          } else {
-            type = 2;
-            p = k < r ? k : r;
-            q = k < r ? r : k;
-          }
-        }
+        const double akk = fabs(s.dg[k]), lam = fabs(s.rowA[r]);
+        need_r = !(akk >= alpha * lam);
       }
       if (lane == 0) {
-        s.piv[0] = type;
+        s.piv[0] = need_r ? -1 : type;
         s.piv[1] = p;
-        s.piv[2] = q;
+        s.piv[2] = need_r ? r : q;
+        s.piv[3] = 0;
       }
     }
     __syncthreads();
+    if (s.piv[0] < 0) {
+      const int r = s.piv[2];
+      current_row(r, s.rowB);
+      __syncthreads();
+      if (warp == 0) {
+        float v = -1.f;
+        int t = 0x7fffffff;
+        for (int j = lane; j < b; j += 32)
+          if (!s.swept[j] && j != r) {
+            const float a = kkt_mag(s.rowB[j]);
+            if (a > v) {
+              v = a;
+              t = j;
+            }
+          }
+        int tt;
+        kkt_argmax32(v, t, tt);
+        const double akk = fabs(s.dg[k]), lam = fabs(s.rowA[r]), sig = fabs(s.rowB[tt]);
+        int type = 1, p, q;
+        if (akk * sig >= alpha * lam * lam) {
+          p = q = k;
+        } else if (fabs(s.dg[r]) >= alpha * sig) {
+          p = q = r;
+        } else {
+          type = 2;
+          p = k < r ? k : r;
+          q = k < r ? r : k;
+        }
+        if (lane == 0) {
+          s.piv[0] = type;
+          s.piv[1] = p;
+          s.piv[2] = q;
+          s.piv[3] = (p == k) ? 0 : 1;      // row p sits in rowA (0) or rowB (1); row q in the other one
+        }
+      }
+      __syncthreads();
+    }
     const int type = s.piv[0], p = s.piv[1], q = s.piv[2];
+    const double* __restrict__ rowp = s.piv[3] ? s.rowB : s.rowA;
+    const double* __restrict__ rowq = s.piv[3] ? s.rowA : s.rowB;
     if (type == 1) {
       double d = s.dg[p];
       if (!(fabs(d) > 1e-250)) {
@@ -133,26 +217,30 @@ __device__ int kktb_sym_invert(double* __restrict__ M, int LD, int b, const KktB
       }
       if (d < 0) nneg++;
       const double di = 1.0 / d;
+      double* __restrict__ C = s.Cg + (size_t)ng * nbb;
+      double* __restrict__ R = s.Rg + (size_t)ng * nbb;
       for (int j = tid; j < b; j += nthreads) {
-        const double a = M[(size_t)p * LD + j];
-        s.c1[j] = (j == p) ? d : (s.swept[j] ? -a : a);     // column p from row p
-        s.r1[j] = (j == p) ? di : a * di;
+        const double a = rowp[j];
+        const double c = (j == p) ? -1.0 : (s.swept[j] ? -a : a);     // column p from row p
+        const double r = (j == p) ? di : a * di;
+        C[j] = c;
+        R[j] = r;
+        s.dg[j] = ((j == p) ? 0.0 : s.dg[j]) - c * r;
+        if (j == p)
+          for (int t = 0; t < ng; ++t) {
+            s.Cg[t * nbb + p] = 0.0;
+            s.Rg[t * nbb + p] = 0.0;
+          }
       }
       __syncthreads();
-      for (int i = warp; i < b; i += nthreads / 32) {
-        const double ci = s.c1[i];
-        double* __restrict__ row = M + (size_t)i * LD;
-        for (int j = lane; j < b; j += 32) {
-          double v = (j == p) ? -ci * di : row[j] - ci * s.r1[j];
-          v = (i == p) ? s.r1[j] : v;
-          row[j] = v;
-          if (i == j) s.dg[i] = v;
-        }
+      if (tid == 0) {
+        s.swept[p] = 1;
+        s.ingrp[p] = 1;
       }
-      if (tid == 0) s.swept[p] = 1;
+      ng += 1;
       remaining -= 1;
     } else {
-      const double epp = s.dg[p], eqq = s.dg[q], epq = M[(size_t)p * LD + q];
+      const double epp = s.dg[p], eqq = s.dg[q], epq = rowp[q];
       double det = epp * eqq - epq * epq;
       if (!(fabs(det) > 1e-250)) {
         det = -1e-250;
@@ -160,41 +248,43 @@ __device__ int kktb_sym_invert(double* __restrict__ M, int LD, int b, const KktB
       }
       nneg += det < 0 ? 1 : (epp + eqq < 0 ? 2 : 0);
       const double i00 = eqq / det, i01 = -epq / det, i11 = epp / det;
+      double* __restrict__ C1 = s.Cg + (size_t)ng * nbb;
+      double* __restrict__ R1 = s.Rg + (size_t)ng * nbb;
+      double* __restrict__ C2 = C1 + nbb;
+      double* __restrict__ R2 = R1 + nbb;
       for (int j = tid; j < b; j += nthreads) {
-        const double ap = M[(size_t)p * LD + j], aq = M[(size_t)q * LD + j];
+        const double ap = rowp[j], aq = rowq[j];
         const double sg = s.swept[j] ? -1.0 : 1.0;
-        s.c1[j] = (j == p) ? epp : ((j == q) ? epq : sg * ap);
-        s.c2[j] = (j == p) ? epq : ((j == q) ? eqq : sg * aq);
+        double c1, c2, r1, r2;
         if (j == p) {
-          s.r1[j] = i00;
-          s.r2[j] = i01;
+          c1 = -1.0; c2 = 0.0; r1 = i00; r2 = i01;
         } else if (j == q) {
-          s.r1[j] = i01;
-          s.r2[j] = i11;
+          c1 = 0.0; c2 = -1.0; r1 = i01; r2 = i11;
         } else {
-          s.r1[j] = i00 * ap + i01 * aq;
-          s.r2[j] = i01 * ap + i11 * aq;
+          c1 = sg * ap; c2 = sg * aq;
+          r1 = i00 * ap + i01 * aq;
+          r2 = i01 * ap + i11 * aq;
         }
+        C1[j] = c1; C2[j] = c2; R1[j] = r1; R2[j] = r2;
+        s.dg[j] = ((j == p || j == q) ? 0.0 : s.dg[j]) - c1 * r1 - c2 * r2;
+        if (j == p || j == q)
+          for (int t = 0; t < ng; ++t) {
+            s.Cg[t * nbb + j] = 0.0;
+            s.Rg[t * nbb + j] = 0.0;
+          }
       }
       __syncthreads();
-      for (int i = warp; i < b; i += nthreads / 32) {
-        const double ca = s.c1[i], cb = s.c2[i];
-        double* __restrict__ row = M + (size_t)i * LD;
-        for (int j = lane; j < b; j += 32) {
-          const double t = ca * s.r1[j] + cb * s.r2[j];
-          double v = (j == p || j == q) ? -t : row[j] - t;
-          v = (i == p) ? s.r1[j] : ((i == q) ? s.r2[j] : v);
-          row[j] = v;
-          if (i == j) s.dg[i] = v;
-        }
-      }
       if (tid == 0) {
         s.swept[p] = 1;
         s.swept[q] = 1;
+        s.ingrp[p] = 1;
+        s.ingrp[q] = 1;
       }
+      ng += 2;
       remaining -= 2;
     }
     __syncthreads();
+    if (ng > RB_KKTB_GRP - 2 || remaining == 0) flush();
   }
   *neg += nneg;
   return bad;
@@ -296,7 +386,7 @@ kkt_factor_solve_big_kernel(const RbKktDev d, const RbKktBatch bt, double* __res
       }
       __syncthreads();
     }
-    bad += kktb_sym_invert(M, LD, b, s, &neg);
+    bad += kktb_sym_invert(M, LD, b, s, &neg, nbb);
     // z = S^-1 y  -> Zs and the X buffer
     kktb_gemm(M, LD, Yr, nrhs, Zs, nrhs, b, b, nrhs, X_g + (size_t)n * bmax * nrhs, nrhs);
     if (n < N - 1) {
@@ -374,7 +464,7 @@ kkt_factor_solve_big_kernel(const RbKktDev d, const RbKktBatch bt, double* __res
     __syncthreads();
     for (int i = tid; i < nb; i += nthreads) {
       Gm[(size_t)i * LD + i] += kkt_diag(v, unkb[i], d.nw);
-      s.c2[i] = rhs[unkb[i]];     // rb (c2 is free outside the inversion)
+      s.rowB[i] = rhs[unkb[i]];     // rb (rowB is free outside the inversion)
     }
     __syncthreads();
     // G -= E' X_E, rb -= E' x_T : thread per (border row j, right-hand-side column r)
@@ -385,11 +475,11 @@ kkt_factor_solve_big_kernel(const RbKktDev d, const RbKktBatch bt, double* __res
         const int e = d.bEc_idx[t];
         acc += kkt_val(v, d.bE_src[e]) * X_g[((size_t)d.bE_blk[e] * bmax + d.bE_row[e]) * nrhs + r];
       }
-      if (r == 0) s.xb[j] = s.c2[j] - acc;     // rb
+      if (r == 0) s.xb[j] = s.rowB[j] - acc;     // rb
       else Gm[(size_t)j * LD + (r - 1)] -= acc;
     }
     __syncthreads();
-    bad += kktb_sym_invert(Gm, LD, nb, s, &neg);
+    bad += kktb_sym_invert(Gm, LD, nb, s, &neg, nbb);
     if (bt.SB)
       for (int i = tid; i < nb * nb; i += nthreads) {
         const int r = i / nb, c = i - r * nb;
@@ -398,7 +488,7 @@ kkt_factor_solve_big_kernel(const RbKktDev d, const RbKktBatch bt, double* __res
     for (int i = tid; i < nb; i += nthreads) {
       double acc = 0.0;
       for (int j = 0; j < nb; ++j) acc += Gm[(size_t)i * LD + j] * s.xb[j];
-      s.c1[i] = acc;
+      s.rowA[i] = acc;
       sol[unkb[i]] = acc;
     }
     __syncthreads();
@@ -413,7 +503,7 @@ kkt_factor_solve_big_kernel(const RbKktDev d, const RbKktBatch bt, double* __res
     const int i = t - d.blk_ptr[lo];
     const double* __restrict__ x = X_g + ((size_t)lo * bmax + i) * nrhs;
     double acc = x[0];
-    for (int j = 0; j < nb; ++j) acc -= x[1 + j] * s.c1[j];
+    for (int j = 0; j < nb; ++j) acc -= x[1 + j] * s.rowA[j];
     sol[d.unk[t]] = acc;
   }
   if (tid == 0 && bt.status) {
