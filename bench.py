@@ -218,6 +218,52 @@ def cpu_iteration_seconds(prod, n_rep=2):
     return t_eval, t_kkt
 
 
+def kkt_kernel_rate(prod, sol, VP, dev):
+    ''' one full wave of the KKT factor/solve kernel on converged C5 iterates, timed with CUDA events, next to its
+    algorithmic flop count (Gauss-Jordan block inverses + the dense products of the sweep) and the FP64 peak '''
+    import torch
+    be = prod.solver._backend
+    K, ks, st = be.K, be.K.ks, prod.structure
+    W = int(be.kkt_wave)
+    T = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
+    reps = -(-W // sol['x'].shape[0])
+    x = T(np.tile(sol['x'], (reps, 1))[:W])
+    lam = T(np.tile(sol['lam_g'], (reps, 1))[:W])
+    vp = T(np.tile(VP, (reps, 1))[:W])
+    be.vp = vp
+    ev = be.eval(x, lam, torch.ones(W, dtype=torch.float64, device=dev), True)
+    dxd = torch.full((W, st.nw), 1e-2, dtype=torch.float64, device=dev)
+    negd = torch.where(torch.as_tensor(st.lbg == st.ubg, device=dev)[None, :], torch.zeros(W, st.ng, dtype=torch.float64, device=dev),
+                       torch.full((W, st.ng), -1.0, dtype=torch.float64, device=dev))
+    rhs = torch.ones(W, st.nw + st.ng, dtype=torch.float64, device=dev)
+    hess, jac = ev['hess'].contiguous(), ev['jac'].contiguous()
+    K.factor_solve(hess, jac, dxd, negd, rhs)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        K.factor_solve(hess, jac, dxd, negd, rhs)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / 3
+    nrhs = 1 + ks.nb
+    flop = 0.0
+    for n in range(ks.N):
+        b = int(ks.blk_ptr[n + 1] - ks.blk_ptr[n])
+        flop += 2.0 * b ** 3 + 2.0 * b * b * nrhs
+        if n < ks.N - 1:
+            m, q = int(ks.cr_ptr[n + 1] - ks.cr_ptr[n]), int(ks.cc_ptr[n + 1] - ks.cc_ptr[n])
+            flop += 2.0 * b * q * m + 2.0 * m * m * q + 2.0 * m * q * nrhs + 2.0 * b * m * nrhs
+    flop += 2.0 * ks.nb ** 3
+    fp = ctypes.c_double(0)
+    prod.functions.lib.rb_fp64_peak(ctypes.byref(fp))
+    return dict(kernel='kkt_factor_solve_kernel<2,4>', instances_per_launch=W, ms_per_launch=ms,
+                factorisations_per_s=W / ms * 1e3, flop_per_factorisation=flop,
+                achieved_tflops=flop * W / (ms * 1e-3) / 1e12, fp64_peak_tflops=fp.value,
+                frac=flop * W / (ms * 1e-3) / 1e12 / fp.value,
+                note='latency bound: 43 dependent Bunch-Kaufman pivot steps per stage block, 489 blocks in sequence per instance')
+
+
 def run_solves(args, dev, rank, world, dist):
     ''' converged raceline solves/s on a multi-start x vehicle-parameter batch of C2 (the C5 shape) '''
     import torch
@@ -271,6 +317,11 @@ def run_solves(args, dev, rank, world, dist):
                return_status_rank0={str(k): int(v) for k, v in zip(*np.unique(np.asarray(s['return_status']), return_counts=True))},
                workload='C5 shape: C2 x multi-start (w0_ws + 0.05*scale*N(0,1)) x vehicle parameters U[0.9,1.1]; '
                         'instance 0 of rank 0 is the nominal race.py problem')
+    if rank == 0:
+        try:
+            out['kkt_kernel'] = kkt_kernel_rate(prod, sol, VP, dev)
+        except Exception as exc:        # a side measurement must not take the bench line down
+            out['kkt_kernel'] = dict(error=repr(exc))
     if rank == 0 and not args.no_cpu:
         t_eval, t_kkt = cpu_iteration_seconds(prod)
         cores = len(os.sched_getaffinity(0))
