@@ -148,13 +148,14 @@ class InteriorPoint:
         res = IpmResult(None, None, None, None, None, None, None, None, None)
         ones_B = torch.ones(B, dtype=dt, device=dev)
 
-        def evaluate(xx, yy, derivs, mask=None):
-            ''' mask: instances whose values are needed (the others keep their previous values) '''
+        def evaluate(xx, yy, derivs, mask=None, prev=None):
+            ''' mask: instances whose values are needed; the other rows keep the values of `prev` (the driver's
+            current evaluation, updated in place -- it survives compaction because the driver owns it) '''
             t0 = time.perf_counter()
             idx = None
             if mask is not None and not bool(mask.all()):
                 idx = torch.nonzero(mask).squeeze(1)
-            out = be.eval(xx, yy, ones_B, derivs, idx)
+            out = be.eval(xx, yy, ones_B, derivs, idx, prev if idx is not None else None)
             if dev.type == 'cuda':
                 torch.cuda.synchronize(dev)
             res.t_eval += time.perf_counter() - t0
@@ -257,6 +258,7 @@ class InteriorPoint:
         iters = torch.zeros(B, dtype=torch.long, device=dev)
         acc_count = torch.zeros(B, dtype=torch.long, device=dev)
         ls_fail = torch.zeros(B, dtype=torch.long, device=dev)
+        moved_prev = torch.ones(B, dtype=torch.bool, device=dev)
         mu_floor = o.tol * o.mu_min_factor
 
         def reset_filter(mask):
@@ -285,7 +287,7 @@ class InteriorPoint:
                 return
             dst = orig[rows_local]
             e_fin = error_at(error_parts(ev, x, s, y, zL, zU, vL, vU), torch.zeros_like(mu))[0]
-            for key, src in (('x', x), ('f', ev['f']), ('g', ev['g']), ('lam_g', y), ('lam_x', zU - zL), ('err', e_fin),
+            for key, src in (('x', torch.minimum(torch.maximum(x, lbx), ubx)), ('f', ev['f']), ('g', ev['g']), ('lam_g', y), ('lam_x', zU - zL), ('err', e_fin),
                              ('status', status), ('iters', iters), ('n_fact', n_fact)):
                 OUT[key][dst] = src[rows_local]
 
@@ -302,8 +304,9 @@ class InteriorPoint:
                  delta_c, first_try, attempts, n_fact, status, iters, acc_count, ls_fail, orig, ones_B, zero_h) = map(sel, (
                      x, s, y, zL, zU, vL, vU, mu, filt_theta, filt_phi, filt_n, theta_max, theta_min, delta_w_last, delta_w,
                      delta_c, first_try, attempts, n_fact, status, iters, acc_count, ls_fail, orig, ones_B, zero_h))
-                (xL, xU, sL, sU, ceq, eq, ineq, fL, fU, sfL, sfU, dampL, dampU, sdampL, sdampU, n_bounds) = map(sel, (
-                    xL, xU, sL, sU, ceq, eq, ineq, fL, fU, sfL, sfU, dampL, dampU, sdampL, sdampU, n_bounds))
+                (xL, xU, sL, sU, ceq, eq, ineq, fL, fU, sfL, sfU, dampL, dampU, sdampL, sdampU, n_bounds, lbx, ubx,
+                 moved_prev) = map(sel, (xL, xU, sL, sU, ceq, eq, ineq, fL, fU, sfL, sfU, dampL, dampU, sdampL, sdampU,
+                                         n_bounds, lbx, ubx, moved_prev))
                 ev = {k_: sel(v_) for k_, v_ in ev.items()}
                 be.select(keep)
                 B = keep.numel()
@@ -314,7 +317,8 @@ class InteriorPoint:
             done = active & (E0 <= o.tol)
             status[done] = 0
             acc = active & ~done & (E0 <= o.acceptable_tol)
-            acc_count = torch.where(acc, acc_count + 1, torch.zeros_like(acc_count))
+            # counted per iteration (like IPOPT), not per sweep: an instance stalled on inertia correction has not moved
+            acc_count = torch.where(acc, acc_count + moved_prev.long(), torch.zeros_like(acc_count))
             done_acc = acc & (acc_count >= o.acceptable_iter)
             status[done_acc] = 1
             active = status == -1
@@ -588,8 +592,11 @@ class InteriorPoint:
                 print(f'      alpha_pr={float(accepted_alpha[0]):.3e} a_max={float(a_pr[0]):.3e} alpha_du={float(a_du[0]):.3e} '
                       f'ls<={ls} failed={bool(failed[0])} theta={float(theta[0]):.3e} dphi={float(dphi[0]):.3e} '
                       f'|dx|={float(dx[0].abs().max()):.2e} |dy|={float(dy[0].abs().max()):.2e} stalled={bool(stalled[0])}')
-            if bool((active & moved).any()):
-                ev = evaluate(x, y, True, active & moved)
+            moved_prev = moved
+            # instances that just ended with "maximum iterations" / "line search failed" took the step too: their
+            # returned f, g and kkt_error belong to the returned x
+            if bool(moved.any()):
+                ev = evaluate(x, y, True, moved, ev)
 
         status[status < 0] = 2
         if OUT:
@@ -600,7 +607,9 @@ class InteriorPoint:
             be.select(None)
         else:
             E0 = errors(ev, x, s, y, zL, zU, vL, vU, torch.zeros_like(mu))[0]
-            res.x, res.f, res.g, res.lam_g = x, ev['f'], ev['g'], y
+            # ipopt.honor_original_bounds = 'yes' (drone3d/raceline/base_raceline.py:788): the returned point lies inside
+            # the original bounds, not the relaxed ones the iterations work with
+            res.x, res.f, res.g, res.lam_g = torch.minimum(torch.maximum(x, lbx), ubx), ev['f'], ev['g'], y
             res.lam_x = zU - zL
             res.status, res.iterations, res.kkt_error = status, iters, E0
             res.factorisations_each = n_fact.cpu().numpy()
@@ -639,25 +648,24 @@ class CudaBackend:
             if getattr(self, '_vp_full', None) is None:
                 self._vp_full = self.vp
             self.vp = self.vp[keep].contiguous()
-        self._buf = {}
 
     def _vp_rows(self, idx):
         return self.vp if (idx is None or self.vp.dim() == 1) else self.vp[idx].contiguous()
 
-    def eval(self, x, lam_g, lam_f, derivs, idx=None):
-        """ idx: evaluate only these instances; the other rows of the returned tensors keep older values """
+    def eval(self, x, lam_g, lam_f, derivs, idx=None, prev=None):
+        """ idx: evaluate only these instances; the other rows keep the values of `prev` (a dict returned by an earlier
+        call, possibly row-compacted by the caller since), which is updated in place and returned """
         st, dev, B = self.st, x.device, x.shape[0]
         f64 = dict(dtype=torch.float64, device=dev)
         names = ('f', 'grad_f', 'g', 'jac', 'hess') if derivs else ('f', 'g')
         shapes = dict(f=(B,), grad_f=(B, st.nw), g=(B, st.ng), jac=(B, st.nnz_jac), hess=(B, st.nnz_hess))
-        tag = 'd_' if derivs else 't_'
-        full = {}
-        for k in names:
-            t = self._buf.get(tag + k)
-            if t is None or tuple(t.shape) != shapes[k] or t.device != dev:
-                t = torch.zeros(shapes[k], **f64)
-                self._buf[tag + k] = t
-            full[k] = t
+        if idx is not None and prev is None:
+            raise ValueError('a masked evaluation needs the previous evaluation to update')
+        if prev is not None:
+            full = {k: prev[k] for k in names}
+            assert all(tuple(full[k].shape) == shapes[k] for k in names)
+        else:
+            full = {k: torch.empty(shapes[k], **f64) for k in names}
         if idx is None:
             xc, lc, out = x.contiguous(), (lam_g.contiguous() if derivs else None), full
         else:
@@ -672,10 +680,7 @@ class CudaBackend:
         if idx is not None:
             for k in names:
                 full[k].index_copy_(0, idx, out[k])
-        if derivs:
-            # the driver keeps these until the next derivative evaluation: hand out the persistent buffers
-            return dict(full)
-        return {k: v.clone() for k, v in full.items()}
+        return dict(full)
 
     def eval_points(self, x_rows, inst):
         """ f and g at arbitrary trial points; inst[r] = instance (vehicle parameters) of row r """

@@ -81,6 +81,19 @@ class KKTStructure:
     # for tests / reference assembly: block id and local index of every KKT unknown
     blk: np.ndarray
     loc: np.ndarray
+    # interface form of the border columns (csrc/kkt_chain.cuh).  Border unknowns are ordered by the first chain
+    # block they couple to, so that at block n the columns 0 .. act[n]-1 are the ones that have appeared so far.
+    # The forward-eliminated border column block Y_n = (L^-1 E)_n is non-zero only on the rows
+    # sup_n = cr_{n-1} U rows(E_n) of block n ("support"); P_n = Y_n[sup_n, :act[n]] is what the kernels carry.
+    act: np.ndarray = None      # [N] active border columns at block n (non-decreasing)
+    sup_ptr: np.ndarray = None  # [N+1]
+    sup: np.ndarray = None      # local row indices (ascending) of the support of block n
+    crs: np.ndarray = None      # [cr_ptr[N]] position of cr_n[a] (a row of block n+1) inside sup_{n+1}
+    bE_sup: np.ndarray = None   # [len(bE_src)] position of bE_row[e] inside sup_n
+    p_off: np.ndarray = None    # [N+1] offset (doubles) of P_n in the factor storage: sup rows x ldq(n)
+    q_off: np.ndarray = None    # [N+1] offset (doubles) of Q_n = S_n^-1[:, sup_n] P_n: b_n rows x ldq(n)
+    amax: int = 0
+    smax: int = 0
 
     @property
     def nk(self):
@@ -97,7 +110,9 @@ class KKTStructure:
                     cr_ptr=self.cr_ptr, cr=self.cr, cc_ptr=self.cc_ptr, cc=self.cc,
                     cL_ptr=self.cL_ptr, cL_src=self.cL_src, cL_pos=self.cL_pos,
                     bE_ptr=self.bE_ptr, bE_src=self.bE_src, bE_row=self.bE_row, bE_col=self.bE_col,
-                    bG_src=self.bG_src, bG_pos=self.bG_pos)
+                    bG_src=self.bG_src, bG_pos=self.bG_pos,
+                    act=self.act, sup_ptr=self.sup_ptr, sup=self.sup, crs=self.crs, bE_sup=self.bE_sup,
+                    p_off=self.p_off, q_off=self.q_off)
 
 
 def _var_stage(st):
@@ -215,8 +230,18 @@ def build_kkt_structure(st) -> KKTStructure:
     if demoted:
         blk[nw + np.array(demoted, dtype=np.int64)] = N
 
-    # local order inside a block: variables (ascending w index) then rows (ascending g index)
-    order = np.lexsort((np.arange(nw + ng), blk))
+    # local order inside a block: variables (ascending w index) then rows (ascending g index); border unknowns by the
+    # first chain block they couple to (unknowns that only couple inside the border last)
+    ei0 = np.concatenate([hr, nw + jr])
+    ej0 = np.concatenate([hc, jc])
+    first = np.zeros(nw + ng, dtype=np.int64)
+    fb = np.full(nw + ng, N, dtype=np.int64)
+    m_i = (blk[ei0] == N) & (blk[ej0] < N)
+    np.minimum.at(fb, ei0[m_i], blk[ej0][m_i])
+    m_j = (blk[ej0] == N) & (blk[ei0] < N)
+    np.minimum.at(fb, ej0[m_j], blk[ei0][m_j])
+    first[blk == N] = fb[blk == N]
+    order = np.lexsort((np.arange(nw + ng), first, blk))
     unk = order.astype(np.int32)
     counts = np.bincount(blk, minlength=N + 1)
     blk_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
@@ -293,7 +318,28 @@ def build_kkt_structure(st) -> KKTStructure:
     bG_src = np.concatenate([g_s, g_s[off]])
 
     i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    # ---- interface form of the border columns -----------------------------------------------------------
+    first_b = first[order[blk_ptr[N]:blk_ptr[N + 1]]]               # per border column, ascending
+    act = np.searchsorted(first_b, np.arange(N), side='right').astype(np.int32)
+    cr_ptr_a, cr_a = np.asarray(cr_ptr), cat(cr_list)
+    sup_list, crs_list, bE_sup = [], [], np.zeros(len(e_src), dtype=np.int32)
+    for n in range(N):
+        rows_e = e_row[bE_ptr[n]:bE_ptr[n + 1]]
+        prev = cr_a[cr_ptr_a[n - 1]:cr_ptr_a[n]] if n > 0 else np.zeros(0, dtype=np.int64)
+        sup_n = np.union1d(prev, rows_e).astype(np.int64)
+        sup_list.append(sup_n)
+        bE_sup[bE_ptr[n]:bE_ptr[n + 1]] = np.searchsorted(sup_n, rows_e)
+        if n > 0:
+            crs_list.append(np.searchsorted(sup_n, prev))
+    crs_list.append(np.zeros(cr_ptr_a[N] - cr_ptr_a[N - 1], dtype=np.int64))      # the last block couples to nothing
+    sup_ptr = np.concatenate([[0], np.cumsum([len(v) for v in sup_list])]).astype(np.int32)
+    ldq = (act + 1) // 2 * 2                                           # even row strides: 16-byte rows for TMA
+    bsz = np.diff(blk_ptr)[:N]
+    p_off = np.concatenate([[0], np.cumsum(np.diff(sup_ptr) * ldq)]).astype(np.int32)
+    q_off = np.concatenate([[0], np.cumsum(bsz * ldq)]).astype(np.int32)
     return KKTStructure(
+        act=act, sup_ptr=sup_ptr, sup=cat(sup_list), crs=cat(crs_list), bE_sup=bE_sup, p_off=p_off, q_off=q_off,
+        amax=int(act.max()) if N else 0, smax=int(np.diff(sup_ptr).max()) if N else 0,
         nw=nw, ng=ng, N=N, nb=nb, bmax=bmax, mmax=mmax, qmax=qmax,
         blk_ptr=blk_ptr, unk=unk, nvar=nvar,
         dA_ptr=dA_ptr, dA_src=i32(dA_src), dA_pos=i32(dA_pos),

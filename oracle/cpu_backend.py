@@ -24,7 +24,13 @@ class OracleBackend:
         self.ng = nlp.ng
         self.nw = nlp.nw
 
-    def eval(self, x, lam_g, lam_f, derivs, idx=None):
+    def eval(self, x, lam_g, lam_f, derivs, idx=None, prev=None):
+        ''' same contract as CudaBackend.eval: with idx, only those rows are evaluated and written into `prev` '''
+        if idx is not None:
+            sub = self.eval(x[idx], None if lam_g is None else lam_g[idx], None if lam_f is None else lam_f[idx], derivs)
+            for k, v in sub.items():
+                prev[k].index_copy_(0, idx, v)
+            return dict(prev)
         B = x.shape[0]
         nlp = self.nlp
         IN = np.zeros((B, nlp.n_in))

@@ -167,3 +167,95 @@ def block_solve(ks, hess, jac, dx_diag, D, rhs, with_inertia=False):
         u = ks.unk[ks.blk_ptr[n]:ks.blk_ptr[n + 1]]
         sol[u] = X[n][:, 0] - (X[n][:, 1:] @ xb if nb else 0.0)
     return (sol, neg) if with_inertia else sol
+
+
+def chain_factor(ks, hess, jac, dx_diag, D):
+    '''
+    numpy twin of kkt_factor_kernel (csrc/kkt_chain.cuh): block LDL' of the chain with the border last.  The border
+    columns are carried in interface form: Y_n = (L^-1 E)_n lives on the support rows sup_n of block n only,
+    P_n = Y_n[sup_n, :act_n];  Q_n = S_n^-1[:, sup_n] P_n;  border Schur complement G - sum_n P_n' Q_n[sup_n].
+    Returns the factor dict and the number of negative eigenvalues.
+    '''
+    N, nb, bmax, qmax, nw = ks.N, ks.nb, ks.bmax, ks.qmax, ks.nw
+    neg_d = -np.asarray(D)
+    diag_of = lambda u: np.where(u < nw, dx_diag[np.minimum(u, nw - 1)], neg_d[np.maximum(u - nw, 0)])
+    val = lambda src: _gather(ks, src, hess, jac, dx_diag, neg_d)
+    F = dict(Sinv=[None] * N, YL=[None] * N, P=[None] * N, Q=[None] * N)
+    neg = 0
+    carry = None
+    Pnext = None
+    Gacc = np.zeros((nb, nb))
+    for n in range(N):
+        u = ks.unk[ks.blk_ptr[n]:ks.blk_ptr[n + 1]]
+        b = len(u)
+        M = np.zeros((bmax, bmax))
+        a, e = ks.dA_ptr[n], ks.dA_ptr[n + 1]
+        M.ravel()[ks.dA_pos[a:e]] = val(ks.dA_src[a:e])
+        M[np.arange(b), np.arange(b)] += diag_of(u)
+        if n > 0:
+            cr = ks.cr[ks.cr_ptr[n - 1]:ks.cr_ptr[n]]
+            M[np.ix_(cr, cr)] -= carry
+        Sinv, ng_ = sym_invert_bp(M[:b, :b])
+        neg += ng_
+        sup = ks.sup[ks.sup_ptr[n]:ks.sup_ptr[n + 1]]
+        an = int(ks.act[n])
+        P = np.zeros((len(sup), an))
+        if n > 0:
+            crs = ks.crs[ks.cr_ptr[n - 1]:ks.cr_ptr[n]]
+            P[crs, :Pnext.shape[1]] = Pnext
+        a, e = ks.bE_ptr[n], ks.bE_ptr[n + 1]
+        np.add.at(P, (ks.bE_sup[a:e], ks.bE_col[a:e]), val(ks.bE_src[a:e]))
+        Q = Sinv[:, sup] @ P
+        Gacc[:an, :an] += P.T @ Q[sup]
+        F['Sinv'][n], F['P'][n], F['Q'][n] = Sinv, P, Q
+        if n < N - 1:
+            cc = ks.cc[ks.cc_ptr[n]:ks.cc_ptr[n + 1]]
+            m = ks.cr_ptr[n + 1] - ks.cr_ptr[n]
+            Lc = np.zeros((max(m, 1), qmax))
+            a, e = ks.cL_ptr[n], ks.cL_ptr[n + 1]
+            Lc.ravel()[ks.cL_pos[a:e]] = val(ks.cL_src[a:e])
+            Lc = Lc[:m, :len(cc)]
+            YL = Sinv[:, cc] @ Lc.T
+            carry = Lc @ YL[cc]
+            Pnext = -YL[sup].T @ P
+            F['YL'][n] = YL
+    if nb:
+        ub = ks.unk[ks.blk_ptr[N]:ks.blk_ptr[N + 1]]
+        G = np.zeros((nb, nb))
+        G.ravel()[ks.bG_pos] = val(ks.bG_src)
+        G[np.arange(nb), np.arange(nb)] += diag_of(ub)
+        F['SB'], ng_ = sym_invert_bp(G - Gacc)
+        neg += ng_
+    return F, int(neg)
+
+
+def chain_solve(ks, F, rhs):
+    ''' numpy twin of kkt_solve_kernel: one right-hand side with the factors of chain_factor '''
+    N, nb = ks.N, ks.nb
+    z = [None] * N
+    rc = None
+    racc = np.zeros(nb)
+    for n in range(N):
+        u = ks.unk[ks.blk_ptr[n]:ks.blk_ptr[n + 1]]
+        y = rhs[u].copy()
+        if n > 0:
+            y[ks.cr[ks.cr_ptr[n - 1]:ks.cr_ptr[n]]] -= rc
+        z[n] = F['Sinv'][n] @ y
+        if n < N - 1:
+            rc = F['YL'][n].T @ y
+        sup = ks.sup[ks.sup_ptr[n]:ks.sup_ptr[n + 1]]
+        racc[:ks.act[n]] += F['P'][n].T @ z[n][sup]
+    sol = np.zeros(ks.nk)
+    xb = np.zeros(0)
+    if nb:
+        ub = ks.unk[ks.blk_ptr[N]:ks.blk_ptr[N + 1]]
+        xb = F['SB'] @ (rhs[ub] - racc)
+        sol[ub] = xb
+    x_next = None
+    for n in range(N - 1, -1, -1):
+        x = z[n] - F['Q'][n] @ xb[:ks.act[n]]
+        if n < N - 1:
+            x -= F['YL'][n] @ x_next[ks.cr[ks.cr_ptr[n]:ks.cr_ptr[n + 1]]]
+        sol[ks.unk[ks.blk_ptr[n]:ks.blk_ptr[n + 1]]] = x
+        x_next = x
+    return sol

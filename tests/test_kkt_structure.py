@@ -28,7 +28,7 @@ def _kkt_inputs(st, nlp, seed):
 @pytest.mark.parametrize('name', RK4_CASES + ['fig8_global_colloc_point', 'fig8_param_colloc_point'])
 def test_block_tables_reproduce_the_sparse_solve(name):
     from oracle.nlp_functions import OracleNLP
-    from oracle.kkt_blocks_ref import kkt_matrix, sparse_solve, block_solve
+    from oracle.kkt_blocks_ref import kkt_matrix, sparse_solve, block_solve, chain_factor, chain_solve
     prod, ref = build_case(name, small=True)
     st = prod.structure
     ks = build_kkt_structure(st)
@@ -46,6 +46,14 @@ def test_block_tables_reproduce_the_sparse_solve(name):
         assert np.abs(K @ sol - rhs).max() <= 1e-9 * max(1.0, np.abs(rhs).max())
         assert np.abs(sol - ref_sol).max() <= 1e-7 * np.abs(ref_sol).max()
         assert neg == int((np.linalg.eigvalsh(K.toarray()) < 0).sum())
+        # interface form of the border columns (the twin of csrc/kkt_chain.cuh): same answer, same inertia
+        F, neg2 = chain_factor(ks, hess, jac, dxd, D)
+        sol2 = chain_solve(ks, F, rhs)
+        for _ in range(2):
+            sol2 = sol2 + chain_solve(ks, F, rhs - K @ sol2)
+        assert neg2 == neg
+        assert np.abs(K @ sol2 - rhs).max() <= 1e-9 * max(1.0, np.abs(rhs).max())
+        assert np.abs(sol2 - ref_sol).max() <= 1e-7 * np.abs(ref_sol).max()
 
 
 def test_full_size_structure_shapes():
