@@ -34,6 +34,9 @@ struct RbKktDev {
   // K v products: CCS (column-wise) and CSR-ordered views of jac_g and of the upper triangle of hess_l
   const int32_t *j_colptr, *j_row, *j_rowptr, *j_col, *j_perm;
   const int32_t *h_colptr, *h_row, *h_rowptr, *h_col, *h_perm;
+  // interface form of the border columns (kkt_chain.cuh; tables documented in kkt.py)
+  int amax, smax;
+  const int32_t *act, *sup_ptr, *sup, *crs, *bE_sup, *p_off, *q_off;
 };
 
 struct RbKktBatch {

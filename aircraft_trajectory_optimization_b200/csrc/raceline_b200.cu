@@ -5,6 +5,7 @@
 // (:160-165): nlp_f, nlp_g, nlp_grad_f, nlp_jac_g, nlp_hess_l.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -25,6 +26,7 @@
 #include "simple_rows.cuh"
 #include "kkt_blocks.cuh"
 #include "kkt_big.cuh"
+#include "kkt_chain.cuh"
 
 namespace {
 

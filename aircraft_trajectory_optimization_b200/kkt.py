@@ -363,6 +363,8 @@ class _KktDesc(ctypes.Structure):
                 + [(k, _i32p) for k in ('blk_ptr', 'unk', 'dA_ptr', 'dA_src', 'dA_pos', 'cr_ptr', 'cr',
                                         'cc_ptr', 'cc', 'cL_ptr', 'cL_src', 'cL_pos', 'bE_ptr', 'bE_src',
                                         'bE_row', 'bE_col', 'bG_src', 'bG_pos')]
+                + [(k, ctypes.c_int) for k in ('amax', 'smax')]
+                + [(k, _i32p) for k in ('act', 'sup_ptr', 'sup', 'crs', 'bE_sup', 'p_off', 'q_off')]
                 + [(k, _i64p) for k in ('jac_colind', 'jac_row', 'hess_colind', 'hess_row')])
 
 
@@ -396,6 +398,7 @@ class KktSolver:
         d = _KktDesc()
         d.nw, d.ng, d.N, d.nb, d.bmax, d.mmax, d.qmax = ks.nw, ks.ng, ks.N, ks.nb, ks.bmax, ks.mmax, ks.qmax
         d.nnz_hess, d.nnz_jac, d.n_bG = st.nnz_hess, st.nnz_jac, len(ks.bG_src)
+        d.amax, d.smax = ks.amax, ks.smax
         for name, arr in ks.tables().items():
             if name == 'nvar':
                 continue

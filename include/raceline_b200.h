@@ -190,6 +190,11 @@ typedef struct rb_kkt_desc {
   const int32_t *cL_ptr, *cL_src, *cL_pos;                /* coupling entries */
   const int32_t *bE_ptr, *bE_src, *bE_row, *bE_col;       /* border columns */
   const int32_t *bG_src, *bG_pos;                         /* border x border */
+  /* interface form of the border columns (stage blocks that fit shared memory): active columns per block,
+   * support rows of block n, position of the coupling rows / border entries inside the support, offsets of the
+   * P_n / Q_n factor blocks */
+  int amax, smax;
+  const int32_t *act, *sup_ptr, *sup, *crs, *bE_sup, *p_off, *q_off;
   const int64_t *jac_colind, *jac_row, *hess_colind, *hess_row;   /* CCS patterns (for K v products) */
 } rb_kkt_desc;
 
