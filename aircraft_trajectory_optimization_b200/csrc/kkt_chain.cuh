@@ -139,9 +139,12 @@ __device__ __noinline__ int kf_sym_invert(double* __restrict__ buf0, double* __r
                                           const double* __restrict__ shift, int LD, int b, KfVec* vec, int* stat) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double alpha = 0.6403882032022076, ralpha = 1.0 / 0.6403882032022076;
+  // the pivot warp of co-resident CTAs should sit on different warp schedulers (warp index mod 4): CTAs that share
+  // an SM usually differ by multiples of the SM count in blockIdx
+  const int pw = (int)((blockIdx.x + blockIdx.x / 148u) & 3u);
   __syncthreads();          // buf0 and shift are complete
   int t = 0;
-  if (warp == 0) {
+  if (warp == pw) {
     // ---------------------------------------------------------------- pivot warp
     // Single-warp critical path of the whole factorisation: kept to ~150 instructions per step in the common case
     // (1 x 1 pivot on the largest diagonal entry; previous update 1 x 1).  Everything else branches off.
@@ -314,7 +317,7 @@ __device__ __noinline__ int kf_sym_invert(double* __restrict__ buf0, double* __r
   } else {
     // ---------------------------------------------------------------- tile warps
     // tile (I, J), I <= J: rows 4 I .. 4 I + 3, columns 4 J .. 4 J + 3; tiles numbered row by row over the upper triangle
-    const int w = tid - 32;
+    const int w = (warp < pw ? warp : warp - 1) * 32 + lane;
     const int nt = (b + 3) >> 2;
     int I = 0, off = 0;
     while (I < nt && w >= off + (nt - I)) {
@@ -392,10 +395,8 @@ __device__ __noinline__ int kf_sym_invert(double* __restrict__ buf0, double* __r
   // mirror the tiles below the diagonal (everything is pivoted now: the inverse is symmetric)
   {
     double* __restrict__ Mr = (t & 1) ? buf1 : buf0;
-    for (int o = tid; o < b * b; o += RB_KF_THREADS) {
-      const int i = o / b, j = o - i * b;
-      if (j < (i & ~3)) Mr[i * LD + j] = Mr[j * LD + i];
-    }
+    for (int i = 4 + warp; i < b; i += RB_KF_THREADS / 32)
+      for (int j = lane; j < (i & ~3); j += 32) Mr[i * LD + j] = Mr[j * LD + i];
   }
   __syncthreads();
   return t & 1;
@@ -595,88 +596,102 @@ kkt_factor_kernel(const RbKktDev d, const RbKktChainBatch bt) {
     double* __restrict__ Qs = YLs + (m > 0 ? (size_t)bmax * mmax : 0);
     const double* __restrict__ Lc = s.Lc;
 
-    // ---- phase A: Q_n = S^-1[:, sup] P_n (b x an) and YL_n = S^-1[:, cc] L_n' (b x m): one row, three columns per
-    // item; S^-1 is read through its symmetry (lanes along a row).  Factor blocks go to global memory as they appear.
+    // ---- phase A: Q_n = S^-1[:, sup] P_n (b x an) and YL_n = S^-1[:, cc] L_n' (b x m).  One row and KA columns per
+    // item: KA independent multiply-add chains per thread (a dependent DFMA takes 23 cycles), S^-1 read through its
+    // symmetry (lanes along a row).  Factor blocks go to global memory as they appear.
     {
-      const int njg = (an + 2) / 3, nag = (m + 2) / 3;
+      constexpr int KA = 9;
+      const int njg = (an + KA - 1) / KA, nag = (m + KA - 1) / KA;
       for (int item = tid; item < b * (njg + nag); item += nth) {
         const int g = item / b, i = item - g * b;
+        double acc[KA];
+#pragma unroll
+        for (int c = 0; c < KA; ++c) acc[c] = 0.0;
         if (g < njg) {
-          const int j0 = g * 3;
-          const int j1 = j0 + 1 < an ? j0 + 1 : j0, j2 = j0 + 2 < an ? j0 + 2 : j0;
-          double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+          const int j0 = g * KA, nc = an - j0 < KA ? an - j0 : KA;
+          const double* __restrict__ pr = s.PA + j0;            // columns beyond an stay inside the padded row
           for (int t = 0; t < sn; ++t) {
             const double sv = Si[sup[t] * LD + i];
-            const double* __restrict__ pr = s.PA + t * ldq;
-            a0 = __fma_rn(sv, pr[j0], a0);
-            a1 = __fma_rn(sv, pr[j1], a1);
-            a2 = __fma_rn(sv, pr[j2], a2);
+#pragma unroll
+            for (int c = 0; c < KA; ++c) acc[c] = __fma_rn(sv, pr[t * ldq + (c < nc ? c : 0)], acc[c]);
           }
-          double* __restrict__ qg = Q_g + rc[KF_REC_QOFF] + (size_t)i * ldq;
-          Qs[i * ldq + j0] = a0;
-          qg[j0] = a0;
-          if (j0 + 1 < an) {
-            Qs[i * ldq + j1] = a1;
-            qg[j1] = a1;
-          }
-          if (j0 + 2 < an) {
-            Qs[i * ldq + j2] = a2;
-            qg[j2] = a2;
-          }
+          double* __restrict__ qg = Q_g + rc[KF_REC_QOFF] + (size_t)i * ldq + j0;
+#pragma unroll
+          for (int c = 0; c < KA; ++c)
+            if (c < nc) {
+              Qs[i * ldq + j0 + c] = acc[c];
+              qg[c] = acc[c];
+            }
         } else {
-          const int a0i = (g - njg) * 3;
-          const int a1i = a0i + 1 < m ? a0i + 1 : a0i, a2i = a0i + 2 < m ? a0i + 2 : a0i;
-          double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+          const int a0 = (g - njg) * KA, nc = m - a0 < KA ? m - a0 : KA;
           for (int t = 0; t < q; ++t) {
             const double sv = Si[cc[t] * LD + i];
-            a0 = __fma_rn(sv, Lc[a0i * qmax + t], a0);
-            a1 = __fma_rn(sv, Lc[a1i * qmax + t], a1);
-            a2 = __fma_rn(sv, Lc[a2i * qmax + t], a2);
+#pragma unroll
+            for (int c = 0; c < KA; ++c) acc[c] = __fma_rn(sv, Lc[(a0 + (c < nc ? c : 0)) * qmax + t], acc[c]);
           }
-          double* __restrict__ yg = YL_g + ((size_t)n * bmax + i) * d.ldY;
-          YLs[i * mmax + a0i] = a0;
-          yg[a0i] = a0;
-          if (a0i + 1 < m) {
-            YLs[i * mmax + a1i] = a1;
-            yg[a1i] = a1;
-          }
-          if (a0i + 2 < m) {
-            YLs[i * mmax + a2i] = a2;
-            yg[a2i] = a2;
-          }
+          double* __restrict__ yg = YL_g + ((size_t)n * bmax + i) * d.ldY + a0;
+#pragma unroll
+          for (int c = 0; c < KA; ++c)
+            if (c < nc) {
+              YLs[i * mmax + a0 + c] = acc[c];
+              yg[c] = acc[c];
+            }
         }
       }
       for (int i = tid; i < sn * ldq; i += nth) P_g[rc[KF_REC_POFF] + i] = s.PA[i];
-      for (int i = tid; i < b * d.ldS; i += nth) {
-        const int r = i / d.ldS, c = i - r * d.ldS;
-        Sinv_g[((size_t)n * bmax + r) * d.ldS + c] = c < b ? Si[r * LD + c] : 0.0;
-      }
+      for (int r = tid >> 5; r < b; r += nth / 32)
+        for (int c = tid & 31; c < d.ldS; c += 32) Sinv_g[((size_t)n * bmax + r) * d.ldS + c] = c < b ? Si[r * LD + c] : 0.0;
     }
     __syncthreads();
     KF_TICK(2);
     // ---- phase B: border Schur complement Gacc[:an, :an] += P_n' Q_n[sup];  carry = L_n YL_n[cc] (m x m);
-    // rows of P_{n+1} that come from this block: -(YL_n[sup])' P_n (m x an)
+    // rows of P_{n+1} that come from this block: -(YL_n[sup])' P_n (m x an).  KB adjacent outputs per item.
     {
-      const int nG = an * an, nC = m * m, nP = m * an;
+      constexpr int KB = 6;
+      const int gG = (an + KB - 1) / KB, gC = (m + KB - 1) / KB;
+      const int nG = an * gG, nC = m * gC, nP = m * gG;
       for (int o = tid; o < nG + nC + nP; o += nth) {
+        double acc[KB];
+#pragma unroll
+        for (int c = 0; c < KB; ++c) acc[c] = 0.0;
         if (o < nG) {
-          const int j1 = o / an, j2 = o - j1 * an;
-          const double g0 = Gacc[j1 * nb + j2];
-          double acc = 0.0;
-          for (int t = 0; t < sn; ++t) acc = __fma_rn(s.PA[t * ldq + j1], Qs[sup[t] * ldq + j2], acc);
-          Gacc[j1 * nb + j2] = g0 + acc;
+          const int j1 = o / gG, j2 = (o - j1 * gG) * KB, nc = an - j2 < KB ? an - j2 : KB;
+          double g0[KB];
+#pragma unroll
+          for (int c = 0; c < KB; ++c) g0[c] = c < nc ? Gacc[j1 * nb + j2 + c] : 0.0;
+          for (int t = 0; t < sn; ++t) {
+            const double pv = s.PA[t * ldq + j1];
+            const double* __restrict__ qr = Qs + sup[t] * ldq + j2;
+#pragma unroll
+            for (int c = 0; c < KB; ++c) acc[c] = __fma_rn(pv, qr[c < nc ? c : 0], acc[c]);
+          }
+#pragma unroll
+          for (int c = 0; c < KB; ++c)
+            if (c < nc) Gacc[j1 * nb + j2 + c] = g0[c] + acc[c];
         } else if (o < nG + nC) {
           const int i = o - nG;
-          const int a = i / m, c = i - a * m;
-          double acc = 0.0;
-          for (int t = 0; t < q; ++t) acc = __fma_rn(Lc[a * qmax + t], YLs[cc[t] * mmax + c], acc);
-          s.carry[a * mmax + c] = acc;
+          const int a = i / gC, c0 = (i - a * gC) * KB, nc = m - c0 < KB ? m - c0 : KB;
+          for (int t = 0; t < q; ++t) {
+            const double lv = Lc[a * qmax + t];
+            const double* __restrict__ yr = YLs + cc[t] * mmax + c0;
+#pragma unroll
+            for (int c = 0; c < KB; ++c) acc[c] = __fma_rn(lv, yr[c < nc ? c : 0], acc[c]);
+          }
+#pragma unroll
+          for (int c = 0; c < KB; ++c)
+            if (c < nc) s.carry[a * mmax + c0 + c] = acc[c];
         } else {
           const int i = o - nG - nC;
-          const int a = i / an, j = i - a * an;
-          double acc = 0.0;
-          for (int t = 0; t < sn; ++t) acc = __fma_rn(YLs[sup[t] * mmax + a], s.PA[t * ldq + j], acc);
-          s.PB[a * ldq + j] = -acc;
+          const int a = i / gG, j0 = (i - a * gG) * KB, nc = an - j0 < KB ? an - j0 : KB;
+          for (int t = 0; t < sn; ++t) {
+            const double yv = YLs[sup[t] * mmax + a];
+            const double* __restrict__ pr = s.PA + t * ldq + j0;
+#pragma unroll
+            for (int c = 0; c < KB; ++c) acc[c] = __fma_rn(yv, pr[c < nc ? c : 0], acc[c]);
+          }
+#pragma unroll
+          for (int c = 0; c < KB; ++c)
+            if (c < nc) s.PB[a * ldq + j0 + c] = -acc[c];
         }
       }
     }

@@ -75,6 +75,61 @@ const VariantInfo kVariants[] = {
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
+// Per-device launch state: the opt-in for large dynamic shared memory is a per-device function attribute, and the side
+// streams / events of the chunked shooting launches belong to the device they were created on.  One entry per CUDA
+// device, created on first use under a mutex (launches on one device from several host threads share the entry;
+// stream-ordered work is serialised by the events, the entry itself is immutable after creation).
+constexpr int kMaxDevices = 64;
+struct DeviceLaunchState {
+  bool ready = false;
+  cudaStream_t side[2] = {nullptr, nullptr};
+  cudaEvent_t ev_in = nullptr, ev_out[2] = {nullptr, nullptr};
+};
+DeviceLaunchState g_dev_state[kMaxDevices];
+std::mutex g_dev_mu;
+
+cudaError_t device_state(DeviceLaunchState** out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+  std::lock_guard<std::mutex> lock(g_dev_mu);
+  DeviceLaunchState& s = g_dev_state[dev];
+  if (!s.ready) {
+    for (int i = 0; i < 2; ++i) {
+      e = cudaStreamCreateWithFlags(&s.side[i], cudaStreamNonBlocking);
+      if (e != cudaSuccess) return e;
+      e = cudaEventCreateWithFlags(&s.ev_out[i], cudaEventDisableTiming);
+      if (e != cudaSuccess) return e;
+    }
+    e = cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+    s.ready = true;
+  }
+  *out = &s;
+  return cudaSuccess;
+}
+
+// largest dynamic shared memory size configured so far for kernel instantiation `Tag`, per device
+template <class Tag>
+cudaError_t ensure_dyn_smem(const void* func, size_t bytes) {
+  static size_t configured[kMaxDevices] = {};
+  static std::mutex mu;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+  std::lock_guard<std::mutex> lock(mu);
+  if (bytes > configured[dev]) {
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    configured[dev] = bytes;
+  }
+  return cudaSuccess;
+}
+template <class PF> struct DirTag {};
+template <class PF> struct CollocTag {};
+
 template <class PF>
 cudaError_t launch_cells_t(const RbDev& d, const RbBatch& b, cudaStream_t st) {
   const long long cells = (long long)b.B * d.N;
@@ -82,26 +137,16 @@ cudaError_t launch_cells_t(const RbDev& d, const RbBatch& b, cudaStream_t st) {
     constexpr int CPB = RB_CELL_THREADS / (PF::NX + 1);
     if (!b.cell_scr) return cudaErrorInvalidValue;
     const size_t dir_smem = Rk4Scratch<PF>::dir_smem_bytes(RB_CELL_THREADS);
-    static bool configured_dir = false;
-    if (!configured_dir) {
-      cudaError_t e = cudaFuncSetAttribute(rk4_dir_kernel<PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dir_smem);
-      if (e != cudaSuccess) return e;
-      configured_dir = true;
-    }
+    cudaError_t e0 = ensure_dyn_smem<DirTag<PF>>((const void*)rk4_dir_kernel<PF>, dir_smem);
+    if (e0 != cudaSuccess) return e0;
     // Chunks alternate between two side streams and the two halves of the scratch, so that the point kernel of
     // chunk i+1 (bound by its scratch writes) overlaps the direction kernel of chunk i (bound by arithmetic).
-    static thread_local cudaStream_t side[2] = {nullptr, nullptr};
-    static thread_local cudaEvent_t ev_in = nullptr, ev_out[2] = {nullptr, nullptr};
-    if (!side[0]) {
-      for (int i = 0; i < 2; ++i) {
-        cudaError_t e = cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking);
-        if (e != cudaSuccess) return e;
-        e = cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming);
-        if (e != cudaSuccess) return e;
-      }
-      cudaError_t e = cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming);
-      if (e != cudaSuccess) return e;
-    }
+    DeviceLaunchState* ds = nullptr;
+    e0 = device_state(&ds);
+    if (e0 != cudaSuccess) return e0;
+    cudaStream_t* side = ds->side;
+    cudaEvent_t ev_in = ds->ev_in;
+    cudaEvent_t* ev_out = ds->ev_out;
     const int nchunk = (b.B + RB_RK4_CHUNK - 1) / RB_RK4_CHUNK;
     const bool fork = nchunk > 1;
     const size_t half = Rk4Scratch<PF>::doubles((long long)RB_RK4_CHUNK * d.N);
@@ -141,12 +186,8 @@ cudaError_t launch_cells_t(const RbDev& d, const RbBatch& b, cudaStream_t st) {
   } else {
     const long long blocks = (cells + RB_COLLOC_WPB - 1) / RB_COLLOC_WPB;
     const size_t smem = sizeof(double) * RB_COLLOC_WPB * (size_t)colloc_cell_doubles<PF>(d.cell_nj, d.cell_nh);
-    static size_t configured = 0;
-    if (smem > configured) {
-      cudaError_t e = cudaFuncSetAttribute(colloc_cells_kernel<PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      configured = smem;
-    }
+    cudaError_t e0 = ensure_dyn_smem<CollocTag<PF>>((const void*)colloc_cells_kernel<PF>, smem);
+    if (e0 != cudaSuccess) return e0;
     colloc_cells_kernel<PF><<<(unsigned)blocks, RB_COLLOC_WPB * 32, smem, st>>>(d, b);
   }
   g_launches++;

@@ -211,7 +211,7 @@ class NlpFunctions:
         self.nlp_jac_g = Function('nlp_jac_g', ['x', 'p'], ['g', 'jac_g_x'], [dx, dp], [dg, self.sp_jac],
                                   lambda x, p=None: tuple(self.eval(x, p, want=('g', 'jac'))[k]
                                                           for k in ('g', 'jac')))
-        self.nlp_hess_l = Function('nlp_hess_l', ['x', 'p', 'lam_f', 'lam_g'], ['hess_gamma_x_x'],
+        self.nlp_hess_l = Function('nlp_hess_l', ['x', 'p', 'lam_f', 'lam_g'], ['triu_hess_gamma_x_x'],
                                    [dx, dp, d1, dg], [self.sp_hess],
                                    lambda x, p=None, lam_f=1.0, lam_g=None:
                                    (self.eval(x, p, lam_f, lam_g, want='hess')['hess'],))
