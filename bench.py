@@ -157,6 +157,23 @@ def cpu_port_rate(seconds_budget=12.0, nthreads=0, sample_intervals=49):
 
 
 
+def cpu_compiled_rate(st, vehicle_config, variant):
+    ''' BASELINE.md plan B: the compiled straight-line port at FULL size (oracle/compiled_cell.py) '''
+    from oracle.compiled_cell import compiled_rate
+    from aircraft_trajectory_optimization_b200.models import vehicle_params
+    r, cores, sample = compiled_rate(st, vehicle_params(vehicle_config), variant)
+    return dict(value=r, unit=UNIT, cores=cores, kind='port', sample=sample)
+
+
+def full_config(st, B, world):
+    ''' the `config` object of the bench line; the reference arm prints the same one '''
+    ab = algorithmic_bytes(st)
+    return dict(workload=WORKLOAD, instances_per_gpu_per_step=B, nw=st.nw, ng=st.ng, nnz_jac=st.nnz_jac,
+                nnz_hess=st.nnz_hess,
+                l2_policy=f'inputs+outputs per step {ab * B / 1e9:.2f} GB per GPU, larger than the 126 MB L2',
+                parallelism=f'{world} x independent instance shards, no collective on the data path')
+
+
 def build_c2_with_warm_start():
     ''' scripts/race.py second solve: parametric quaternion drone, RK4, warm-started from the point-mass solve '''
     from cases import make_line
@@ -215,7 +232,16 @@ def cpu_iteration_seconds(prod, n_rep=2):
     for _ in range(n_rep):
         spla.splu(K).solve(np.ones(st.nw + st.ng))
     t_kkt = (time.perf_counter() - t0) / n_rep
-    return t_eval, t_kkt
+    # the same evaluation through compiled straight-line code, full size, one core (oracle/compiled_cell.py)
+    t_eval_c = None
+    try:
+        from oracle.compiled_cell import compiled_rate
+        from aircraft_trajectory_optimization_b200.models import vehicle_params
+        r, _, _ = compiled_rate(st, vehicle_params(prod.vehicle_config), prod.model.variant, seconds_budget=3.0, nthreads=1)
+        t_eval_c = 1.0 / r
+    except Exception:
+        pass
+    return t_eval, t_kkt, t_eval_c
 
 
 def kkt_kernel_rate(prod, sol, VP, dev):
@@ -246,22 +272,28 @@ def kkt_kernel_rate(prod, sol, VP, dev):
     e1.record()
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1) / 3
-    nrhs = 1 + ks.nb
+    # algorithmic flops of kkt_factor_kernel + kkt_solve_kernel (csrc/kkt_chain.cuh): Gauss-Jordan inverse of the upper
+    # triangle (b^3), Q_n, YL_n, carry, P_{n+1}, border Schur complement; one solve = forward + backward products
     flop = 0.0
     for n in range(ks.N):
         b = int(ks.blk_ptr[n + 1] - ks.blk_ptr[n])
-        flop += 2.0 * b ** 3 + 2.0 * b * b * nrhs
+        sn, an = int(ks.sup_ptr[n + 1] - ks.sup_ptr[n]), int(ks.act[n])
+        flop += 1.0 * b ** 3 + 2.0 * b * sn * an + 2.0 * an * an * sn
+        flop += 2.0 * b * b + 2.0 * sn * an + 2.0 * b * an                       # solve: z, r_b, Q x_b
         if n < ks.N - 1:
             m, q = int(ks.cr_ptr[n + 1] - ks.cr_ptr[n]), int(ks.cc_ptr[n + 1] - ks.cc_ptr[n])
-            flop += 2.0 * b * q * m + 2.0 * m * m * q + 2.0 * m * q * nrhs + 2.0 * b * m * nrhs
-    flop += 2.0 * ks.nb ** 3
+            flop += 2.0 * b * q * m + 2.0 * m * m * q + 2.0 * m * sn * an
+            flop += 4.0 * b * m                                                  # solve: carry, back-substitution
+    flop += 1.0 * ks.nb ** 3
     fp = ctypes.c_double(0)
     prod.functions.lib.rb_fp64_peak(ctypes.byref(fp))
-    return dict(kernel='kkt_factor_solve_kernel<2,4>', instances_per_launch=W, ms_per_launch=ms,
+    return dict(kernel='kkt_factor_kernel + kkt_solve_kernel', instances_per_launch=W, ms_per_launch=ms,
                 factorisations_per_s=W / ms * 1e3, flop_per_factorisation=flop,
                 achieved_tflops=flop * W / (ms * 1e-3) / 1e12, fp64_peak_tflops=fp.value,
+                fp64_peak_source='rb_fp64_peak micro-kernel in this run (MEASURED_PEAKS.json has no fp64 entry)',
                 frac=flop * W / (ms * 1e-3) / 1e12 / fp.value,
-                note='latency bound: 43 dependent Bunch-Kaufman pivot steps per stage block, 489 blocks in sequence per instance')
+                note='latency bound: ~41 dependent Bunch-Kaufman pivot steps per stage block (one pivot warp, ~190 '
+                     'instructions per step), 489 blocks in sequence per instance; dependent DFMA latency is 23 cycles')
 
 
 def run_solves(args, dev, rank, world, dist):
@@ -312,6 +344,12 @@ def run_solves(args, dev, rank, world, dist):
                t_eval_s=s['t_wall_nlp_hess_l'], t_kkt_s=s['t_wall_linear_solver'],
                lap_time_nominal=float(laps[0]), lap_time_min=float(laps[okf].min()) if okf.any() else None,
                lap_time_max=float(laps[okf].max()) if okf.any() else None,
+               e2e=dict(value=float(t[1]) / float(t[0]), unit='converged solves/s',
+                        api='solver(x0=, lbx=, ubx=, lbg=, ubg=, p=) with HOST arrays in and out (integration level A: the '
+                            'interior-point driver runs on the device, only x0 / vehicle parameters go in and '
+                            'x, f, g, lam_g, lam_x, status come back)',
+                        h2d_bytes_per_step=int(8 * B * (st.nw + VP.shape[1]) + 8 * 2 * (st.nw + st.ng)),
+                        d2h_bytes_per_step=int(8 * B * (2 * st.nw + 2 * st.ng + 3))),
                warm_start_setup_s=t_build, gpu_launches=int(prod.functions.launch_count() - lib_launch0),
                speculative_factorisations=int(prod.solver.result.n_speculated),
                return_status_rank0={str(k): int(v) for k, v in zip(*np.unique(np.asarray(s['return_status']), return_counts=True))},
@@ -323,7 +361,7 @@ def run_solves(args, dev, rank, world, dist):
         except Exception as exc:        # a side measurement must not take the bench line down
             out['kkt_kernel'] = dict(error=repr(exc))
     if rank == 0 and not args.no_cpu:
-        t_eval, t_kkt = cpu_iteration_seconds(prod)
+        t_eval, t_kkt, t_eval_c = cpu_iteration_seconds(prod)
         cores = len(os.sched_getaffinity(0))
         its = out['iterations_median'] or out['iterations_max']
         # IPOPT on this problem class: ~1.5 function evaluations and (measured here, inertia retries included)
@@ -331,11 +369,56 @@ def run_solves(args, dev, rank, world, dist):
         fac_per_it = float(np.mean(prod.solver.result.factorisations_each / np.maximum(1, s['iterations_each'])))
         per_solve = its * (t_eval * 1.5 + t_kkt * fac_per_it)
         out['cpu_baseline'] = dict(value=cores / per_solve, unit='converged solves/s', cores=cores, kind='port',
-                                   sample=f'one IP iteration on one core: tape evaluation {t_eval * 1e3:.1f} ms (49-interval '
-                                          f'sample x10) + SuperLU factor/solve of the {st.nw + st.ng}-dim KKT matrix '
-                                          f'{t_kkt * 1e3:.1f} ms x {fac_per_it:.2f} factorisations/iteration; x {its:.0f} '
-                                          f'iterations (median of the GPU run); one solve per core on {cores} cores')
+                                   modelled=True,
+                                   sample=f'MODELLED from measured parts (no CPU interior-point run at full size: the full-size '
+                                          f'tape takes minutes to build): one IP iteration on one core = tape evaluation '
+                                          f'{t_eval * 1e3:.1f} ms (49-interval sample x10) + SuperLU factor/solve of the full '
+                                          f'{st.nw + st.ng}-dim KKT matrix {t_kkt * 1e3:.1f} ms x {fac_per_it:.2f} '
+                                          f'factorisations/iteration; x {its:.0f} iterations (median of the GPU run); one solve '
+                                          f'per core on {cores} cores')
+        if t_eval_c is not None:
+            per_solve_c = its * (t_eval_c * 1.5 + t_kkt * fac_per_it)
+            out['cpu_baseline']['compiled'] = dict(
+                value=cores / per_solve_c, unit='converged solves/s', modelled=True,
+                sample=f'the same with the compiled straight-line evaluation, full size: {t_eval_c * 1e3:.2f} ms per evaluation')
     return out
+
+
+def run_colloc_eval(dev, local_rank, steps, B=512):
+    ''' C1 (scripts/fig_8.py: global-frame quaternion drone, Legendre collocation N=56, K=7): device-resident evals/s '''
+    import torch
+    from cases import build_product
+    from aircraft_trajectory_optimization_b200.functions import NlpFunctions, load_library
+    from aircraft_trajectory_optimization_b200.models import vehicle_params
+    prod = build_product('fig8_global_colloc_drone')
+    st = prod.structure
+    F = NlpFunctions(st, prod.vehicle_config, device=local_rank)
+    lib = load_library()
+    X, L, VP = make_inputs(st, vehicle_params(prod.vehicle_config), B, seed0=0)
+    f64 = dict(dtype=torch.float64, device=dev)
+    x_d, l_d, vp_d = (torch.from_numpy(a).to(dev) for a in (X, L, VP))
+    sig_d = torch.ones(B, **f64)
+    outs = [torch.empty(B, **f64), torch.empty(B, st.nw, **f64), torch.empty(B, st.ng, **f64),
+            torch.empty(B, st.nnz_jac, **f64), torch.empty(B, st.nnz_hess, **f64)]
+    scratch = torch.empty(max(1, lib.rb_eval_scratch_bytes(F.handle, B)), dtype=torch.uint8, device=dev)
+    step = lambda: F.eval_device(x_d, l_d, sig_d, vp_d, None, *outs, scratch)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    ab = algorithmic_bytes(st)
+    peak, _ = _peaks()
+    return dict(workload='C1: scripts/fig_8.py, global-frame quaternion drone, Legendre collocation N=56 K=7',
+                value=B / (ms * 1e-3), unit=UNIT, instances_per_step=B, ms_per_step=ms, nw=st.nw, ng=st.ng,
+                nnz_jac=st.nnz_jac, nnz_hess=st.nnz_hess, algorithmic_bytes_per_eval=ab,
+                roofline=dict(bound='hbm', achieved=ab * B / (ms * 1e-3) / 1e9, peak=peak, unit='GB/s',
+                              frac=ab * B / (ms * 1e-3) / 1e9 / peak, kernel='colloc_cells_kernel<PF_drone_quat_global>'))
 
 
 def run_reference(args):
@@ -351,11 +434,18 @@ def run_reference(args):
         if i >= args.warmup:
             rates.append(r)
     v = float(np.mean(rates))
+    from cases import build_product
+    prod = build_product(CASE)                      # host-side structure only: sizes for the shared config object
+    cpu = dict(value=v, unit=UNIT, cores=cores, kind='port', sample=sample)
+    try:
+        cpu['compiled'] = cpu_compiled_rate(prod.structure, prod.vehicle_config, prod.model.variant)
+    except Exception as exc:
+        cpu['compiled'] = dict(error=repr(exc))
     line = dict(impl='reference', metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1e3 * (time.time() - t0) / max(1, args.steps + args.warmup),
                 higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64', data='synthetic',
-                config=dict(workload=WORKLOAD),
-                cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind='port', sample=sample),
+                config=full_config(prod.structure, args.batch, args.gpus),
+                cpu_baseline=cpu,
                 e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
 
@@ -370,6 +460,7 @@ def main():
     ap.add_argument('--e2e-batch', type=int, default=256)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-solves', action='store_true', help='skip the converged-solves leg')
+    ap.add_argument('--no-colloc', action='store_true', help='skip the C1 (collocation) evaluation leg')
     ap.add_argument('--solves-batch', type=int, default=2048, help='multi-start instances per GPU in the solves leg')
     ap.add_argument('--solves-window', type=int, default=888, help='instances iterating at a time (continuous batching)')
     ap.add_argument('--solves-refine', type=int, default=1, help='iterative-refinement steps per KKT solve')
@@ -488,6 +579,12 @@ def main():
     # spot check: the host path and the device path agree bit for bit on instance 0
     assert np.array_equal(hh[0].numpy(), h_d[0].cpu().numpy()) and np.array_equal(hj[0].numpy(), j_d[0].cpu().numpy())
 
+    colloc = None
+    if rank == 0 and not args.no_colloc:
+        try:
+            colloc = run_colloc_eval(dev, local_rank, max(3, args.steps // 2))
+        except Exception as exc:        # a side measurement must not take the bench line down
+            colloc = dict(error=repr(exc))
     solves = None
     if not args.no_solves:
         del x_d, l_d, j_d, h_d, gf_d, g_d
@@ -524,17 +621,21 @@ def main():
         cpu = None
         if not args.no_cpu:
             r, cores, sample = cpu_port_rate()
-            cpu = dict(value=r, unit=UNIT, cores=cores, kind='port', sample=sample)
+            cpu = dict(value=r, unit=UNIT, cores=cores, kind='port', sample=sample,
+                       note='value = the execution model the reference runs (interpreted SX tape); `compiled` = what '
+                            'C code generation of the same interval function gives, full size, no scaling')
+            try:
+                cpu['compiled'] = cpu_compiled_rate(st, prod.vehicle_config, prod.model.variant)
+            except Exception as exc:
+                cpu['compiled'] = dict(error=repr(exc))
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=total_ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
                     dtype='f64', data='synthetic',
-                    config=dict(workload=WORKLOAD, instances_per_gpu_per_step=B, nw=st.nw, ng=st.ng,
-                                nnz_jac=st.nnz_jac, nnz_hess=st.nnz_hess,
-                                l2_policy=f'inputs+outputs per step {ab * B / 1e9:.2f} GB per GPU, larger than the 126 MB L2',
-                                parallelism=f'{world} x independent instance shards, no collective on the data path'),
+                    config=full_config(st, B, world),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              instances_per_step=Be, api='rb_nlp_eval_all (host buffers, pinned)'),
-                    gpu_launches=launches, clocks=clocks, roofline=roofline, cpu_baseline=cpu, solves=solves)
+                    gpu_launches=launches, clocks=clocks, roofline=roofline, cpu_baseline=cpu, solves=solves,
+                    collocation=colloc)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
