@@ -39,6 +39,13 @@ COMPILED_VARIANTS = [
     Variant('point', 'quat', 'param_gr', False),
     Variant('drone', 'ypr', 'param_gr', False),
     Variant('drone', 'ypr', 'global', False),
+    # frame-relative orientation (`global_r=False`, drone3d/dynamics/drone_models.py:249-292, point_model.py:149-213)
+    Variant('drone', 'quat', 'param_lr', False),
+    Variant('drone', 'ypr', 'param_lr', False),
+    Variant('point', 'quat', 'param_lr', False),
+    # linear drag b != 0 changes the sparsity pattern: the two BASELINE drone variants with drag
+    Variant('drone', 'quat', 'global', True),
+    Variant('drone', 'quat', 'param_gr', True),
 ]
 
 
@@ -312,7 +319,8 @@ def generate_all(variants=None, out_dir=GEN_DIR, verbose=False):
 def load_meta(variant: Variant, out_dir=GEN_DIR):
     path = os.path.join(out_dir, f'pf_{variant.name}.json')
     if not os.path.exists(path):
-        raise FileNotFoundError(f'{path} missing: run __graft_entry__.build() / codegen.generate_all()')
+        # generated files are build outputs (not tracked): regenerate on demand (a few seconds per variant)
+        generate_variant(variant, out_dir)
     with open(path) as fh:
         return json.load(fh)
 

@@ -21,6 +21,11 @@
 #include "generated/pf_drone_ypr_param_gr.cuh"
 #include "generated/pf_point_pm_global.cuh"
 #include "generated/pf_point_pm_param_gr.cuh"
+#include "generated/pf_drone_quat_param_lr.cuh"
+#include "generated/pf_drone_ypr_param_lr.cuh"
+#include "generated/pf_point_pm_param_lr.cuh"
+#include "generated/pf_drone_quat_global_drag.cuh"
+#include "generated/pf_drone_quat_param_gr_drag.cuh"
 #include "rk4_cells2.cuh"
 #include "colloc_cells.cuh"
 #include "simple_rows.cuh"
@@ -72,6 +77,12 @@ const VariantInfo kVariants[] = {
     {"point_pm_param_gr", PF_point_pm_param_gr::NZ, PF_point_pm_param_gr::NU, PF_point_pm_param_gr::NVP, Rk4Scratch<PF_point_pm_param_gr>::NS, PF_point_pm_param_gr::CPB},
     {"drone_ypr_param_gr", PF_drone_ypr_param_gr::NZ, PF_drone_ypr_param_gr::NU, PF_drone_ypr_param_gr::NVP, Rk4Scratch<PF_drone_ypr_param_gr>::NS, PF_drone_ypr_param_gr::CPB},
     {"drone_ypr_global", PF_drone_ypr_global::NZ, PF_drone_ypr_global::NU, PF_drone_ypr_global::NVP, Rk4Scratch<PF_drone_ypr_global>::NS, PF_drone_ypr_global::CPB},
+#define RB_VARIANT(PF, name) {name, PF::NZ, PF::NU, PF::NVP, Rk4Scratch<PF>::NS, PF::CPB}
+    RB_VARIANT(PF_drone_quat_param_lr, "drone_quat_param_lr"),
+    RB_VARIANT(PF_drone_ypr_param_lr, "drone_ypr_param_lr"),
+    RB_VARIANT(PF_point_pm_param_lr, "point_pm_param_lr"),
+    RB_VARIANT(PF_drone_quat_global_drag, "drone_quat_global_drag"),
+    RB_VARIANT(PF_drone_quat_param_gr_drag, "drone_quat_param_gr_drag"),
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
@@ -202,6 +213,11 @@ cudaError_t launch_cells(int variant, const RbDev& d, const RbBatch& b, cudaStre
     case 3: return launch_cells_t<PF_point_pm_param_gr>(d, b, st);
     case 4: return launch_cells_t<PF_drone_ypr_param_gr>(d, b, st);
     case 5: return launch_cells_t<PF_drone_ypr_global>(d, b, st);
+    case 6: return launch_cells_t<PF_drone_quat_param_lr>(d, b, st);
+    case 7: return launch_cells_t<PF_drone_ypr_param_lr>(d, b, st);
+    case 8: return launch_cells_t<PF_point_pm_param_lr>(d, b, st);
+    case 9: return launch_cells_t<PF_drone_quat_global_drag>(d, b, st);
+    case 10: return launch_cells_t<PF_drone_quat_param_gr_drag>(d, b, st);
   }
   return cudaErrorInvalidValue;
 }

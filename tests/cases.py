@@ -67,14 +67,37 @@ CASES = {
 }
 
 
+# variants of the cases above with other vehicle settings: name -> (base case, vehicle keyword arguments).
+# `global_r=False`: orientation relative to the centerline frame (drone3d/dynamics/drone_models.py:249-292,
+# point_model.py:149-213; exposed by drone3d/utils/solve_util.py:11-24); b != 0: linear drag changes the pattern.
+VARIANT_CASES = {
+    'fig8_param_colloc_drone_lr': ('fig8_param_colloc_drone', dict(global_r=False)),
+    'race_param_rk4_drone_lr': ('race_param_rk4_drone', dict(global_r=False)),
+    'race_param_rk4_drone_euler_lr': ('race_param_rk4_drone_euler', dict(global_r=False)),
+    'race_param_rk4_point_lr': ('race_param_rk4_point', dict(global_r=False)),
+    'fig8_param_colloc_point_lr': ('fig8_param_colloc_point', dict(global_r=False)),
+    'race_param_rk4_drone_drag': ('race_param_rk4_drone', dict(b1=0.05, b2=0.07, b3=0.02)),
+    'fig8_global_colloc_drone_drag': ('fig8_global_colloc_drone', dict(b1=0.05, b2=0.07, b3=0.02)),
+}
+
+
+def _resolve(name, vehicle_kw):
+    if name in VARIANT_CASES:
+        base, kw = VARIANT_CASES[name]
+        return base, {**kw, **(vehicle_kw or {})}
+    return name, vehicle_kw
+
+
 def vehicle_config(vehicle, quat=True, tube=False, **kw):
     rc = dict(collision_radius=0.4) if tube else {}
+    kw = {'global_r': True, **kw}
     if vehicle == 'drone':
-        return DroneConfig(global_r=True, use_quat=quat, **rc, **kw)
-    return PointConfig(global_r=True, **rc, **kw)
+        return DroneConfig(use_quat=quat, **rc, **kw)
+    return PointConfig(**rc, **kw)
 
 
 def build_product(name, small=False, N=None, vehicle_kw=None):
+    name, vehicle_kw = _resolve(name, vehicle_kw)
     track, frame, vehicle, rk4, n_full, n_small, quat, tube = CASES[name]
     N = N or (n_small if small else n_full)
     line = make_line(track)
@@ -109,6 +132,7 @@ def build_product(name, small=False, N=None, vehicle_kw=None):
 def build_oracle(name, small=False, N=None, vehicle_kw=None):
     from oracle.ref_centerline import RefSplineCenterline
     from oracle.ref_raceline import RefRaceline, RefTube
+    name, vehicle_kw = _resolve(name, vehicle_kw)
     track, frame, vehicle, rk4, n_full, n_small, quat, tube = CASES[name]
     N = N or (n_small if small else n_full)
     line = make_line(track, RefSplineCenterline)

@@ -5,7 +5,7 @@ the same seeded inputs.  fp64; tolerance 1e-10 relative (BASELINE.json north_sta
 import numpy as np
 import pytest
 
-from cases import CASES, build_case, eval_point
+from cases import CASES, VARIANT_CASES, build_case, eval_point
 
 RTOL = 1e-10
 RK4_CASES = [c for c, v in CASES.items() if v[3]]
@@ -58,6 +58,13 @@ def test_rk4_parity(name, built_library):
 @pytest.mark.gpu
 @pytest.mark.parametrize('name', COLLOC_CASES)
 def test_collocation_parity(name, built_library):
+    _check_case(name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', list(VARIANT_CASES))
+def test_variant_parity(name, built_library):
+    ''' frame-relative orientation (global_r=False) and linear-drag variants '''
     _check_case(name)
 
 

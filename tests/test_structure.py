@@ -8,12 +8,12 @@ import os
 import numpy as np
 import pytest
 
-from cases import CASES, build_case, build_product
+from cases import CASES, VARIANT_CASES, build_case, build_product
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 
-@pytest.mark.parametrize('name', list(CASES))
+@pytest.mark.parametrize('name', list(CASES) + list(VARIANT_CASES))
 def test_structure_matches_oracle(name, built_library):
     from oracle.nlp_functions import OracleNLP
     prod, ref = build_case(name, small=True)
