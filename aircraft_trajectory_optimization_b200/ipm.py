@@ -17,8 +17,17 @@ independent problem instances of one structure advance in lock step:
     matrix; a wrong inertia (not exactly ng negative eigenvalues) or a vanishing pivot triggers
     IPOPT's delta_w / delta_c escalation schedule (Algorithm IC of the paper);
   * monotone barrier update, fraction-to-the-boundary rule, filter with switching / Armijo
-    conditions; no restoration phase (a failed line search resets the filter and takes the
-    shortest trial step; three failures in a row mark the instance as failed).
+    conditions;
+  * feasibility restoration (IPOPT switches to it when the line search cannot make progress): the
+    instance leaves the filter method and minimises the constraint violation from the reference
+    point x_R where it got stuck,
+        min  rho/2 ||c(x, s)||^2 + zeta/2 ||D_R (x - x_R)||^2 - mu sum log(distance to the bounds),
+    by regularised Gauss-Newton steps -- the same KKT kernel with W = 0, diagonal -1/rho on every row
+    (quasi-definite: always the right inertia, also where the Jacobian is rank deficient) and an
+    Armijo search on that merit function -- until theta has dropped by the factor resto_kappa and
+    the point is acceptable to the original filter; multipliers are reset on return.  (IPOPT's
+    own restoration problem uses the l1 norm with extra slack variables; the l2 form needs no new
+    unknowns and no new kernel.)
 
 All state lives in torch tensors on the device of the inputs; the two heavy operations come from a
 *backend* object (`eval`, `kkt_solve`, `kkt_matvec`).  The product backend is `CudaBackend`
@@ -66,13 +75,17 @@ class IpmOptions:
     kappa_w_plus_first: float = 100.0
     delta_c_bar: float = 1e-8
     kappa_c: float = 0.25
-    refine_steps: int = 1               # IPOPT min_refinement_steps; further steps change neither the iteration counts nor
-                                       # the converged fraction of the C5 batch, each costs ~8 ms per 444-instance wave
+    refine_steps: int = 4               # at most this many refinement steps per solve; a step is taken only while some
+                                       # instance's scaled residual is above refine_tol (IPOPT: residual_ratio_max 1e-10)
     compact: bool = True               # copy the surviving instances into smaller tensors once few are left
     compact_frac: float = 0.5
     compact_min: int = 16
     speculate: int = 2                 # spare slots of a factorisation wave try this many further delta_w candidates
     speculate_max: int = 4             # ... up to this many when the wave is mostly empty
+    restoration: bool = True           # feasibility restoration when the line search fails (see below)
+    resto_kappa: float = 0.9           # leave restoration once theta <= resto_kappa * theta at entry
+    resto_rho: float = 1e4             # weight of the constraint violation in the restoration merit (IPOPT: rho = 1000 on the l1 norm)
+    resto_max_iter: int = 200          # restoration iterations per visit before the instance is given up
     window: int = 0                    # > 0: at most this many instances iterate at a time; finished ones are
                                        # replaced from the pending queue (keeps the batched kernels full)
     verbose: bool = False
@@ -93,6 +106,7 @@ class IpmResult:
     n_eval: int = 0
     n_factor: int = 0
     n_speculated: int = 0              # extra delta_w candidates factorised in spare wave slots
+    n_restorations: int = 0            # visits of the feasibility restoration, summed over the instances
     t_eval: float = 0.0
     t_kkt: float = 0.0
     t_total: float = 0.0
@@ -259,6 +273,12 @@ class InteriorPoint:
         acc_count = torch.zeros(B, dtype=torch.long, device=dev)
         ls_fail = torch.zeros(B, dtype=torch.long, device=dev)
         moved_prev = torch.ones(B, dtype=torch.bool, device=dev)
+        resto = torch.zeros(B, dtype=torch.bool, device=dev)             # in feasibility restoration
+        resto_it = torch.zeros(B, dtype=torch.long, device=dev)
+        theta_R = torch.zeros(B, dtype=dt, device=dev)                   # theta at entry
+        x_R = x.clone()                                                  # reference point of the restoration
+        DR2 = torch.ones_like(x)                                         # D_R^2 = 1 / max(1, |x_R|)^2
+        n_resto = torch.zeros(B, dtype=torch.long, device=dev)           # restoration visits per instance
         mu_floor = o.tol * o.mu_min_factor
 
         def reset_filter(mask):
@@ -301,9 +321,11 @@ class InteriorPoint:
                 keep = torch.nonzero(live).squeeze(1)
                 sel = lambda t_: t_[keep].contiguous()
                 (x, s, y, zL, zU, vL, vU, mu, filt_theta, filt_phi, filt_n, theta_max, theta_min, delta_w_last, delta_w,
-                 delta_c, first_try, attempts, n_fact, status, iters, acc_count, ls_fail, orig, ones_B, zero_h) = map(sel, (
+                 delta_c, first_try, attempts, n_fact, status, iters, acc_count, ls_fail, orig, ones_B, zero_h,
+                 resto, resto_it, theta_R, x_R, DR2, n_resto) = map(sel, (
                      x, s, y, zL, zU, vL, vU, mu, filt_theta, filt_phi, filt_n, theta_max, theta_min, delta_w_last, delta_w,
-                     delta_c, first_try, attempts, n_fact, status, iters, acc_count, ls_fail, orig, ones_B, zero_h))
+                     delta_c, first_try, attempts, n_fact, status, iters, acc_count, ls_fail, orig, ones_B, zero_h,
+                     resto, resto_it, theta_R, x_R, DR2, n_resto))
                 (xL, xU, sL, sU, ceq, eq, ineq, fL, fU, sfL, sfU, dampL, dampU, sdampL, sdampU, n_bounds, lbx, ubx,
                  moved_prev) = map(sel, (xL, xU, sL, sU, ceq, eq, ineq, fL, fU, sfL, sfU, dampL, dampU, sdampL, sdampU,
                                          n_bounds, lbx, ubx, moved_prev))
@@ -311,12 +333,26 @@ class InteriorPoint:
                 be.select(keep)
                 B = keep.numel()
                 active = status == -1
+            # ---- leave the restoration: theta has dropped by resto_kappa and the filter accepts the point --------
+            if bool((resto & active).any()):
+                th0 = infeas(ev['g'], s).abs().sum(1)
+                ph0 = barrier(ev['f'], x, s, mu)
+                in_f = ((th0[:, None] >= (1 - o.gamma_theta) * filt_theta)
+                        & (ph0[:, None] >= filt_phi - o.gamma_phi * filt_theta)).any(1)
+                leave = resto & active & (th0 <= o.resto_kappa * theta_R) & ~in_f
+                if bool(leave.any()):
+                    lv = leave[:, None]
+                    resto = resto & ~leave
+                    y = torch.where(lv, torch.zeros_like(y), y)            # multipliers restart; the kappa_sigma
+                    zL, zU = torch.where(lv, fL, zL), torch.where(lv, fU, zU)      # safeguard pulls z towards mu / d
+                    vL, vU = torch.where(lv, sfL, vL), torch.where(lv, sfU, vU)
+                    ev = evaluate(x, y, True, leave, ev)                   # hess_l with the new multipliers
             # ---- convergence and barrier update --------------------------------------------------------
             parts = error_parts(ev, x, s, y, zL, zU, vL, vU)
             E0, dual0, prim0, comp0 = error_at(parts, torch.zeros_like(mu))
-            done = active & (E0 <= o.tol)
+            done = active & ~resto & (E0 <= o.tol)
             status[done] = 0
-            acc = active & ~done & (E0 <= o.acceptable_tol)
+            acc = active & ~resto & ~done & (E0 <= o.acceptable_tol)
             # counted per iteration (like IPOPT), not per sweep: an instance stalled on inertia correction has not moved
             acc_count = torch.where(acc, acc_count + moved_prev.long(), torch.zeros_like(acc_count))
             done_acc = acc & (acc_count >= o.acceptable_iter)
@@ -340,7 +376,7 @@ class InteriorPoint:
                 break
             for _ in range(4):
                 Emu = error_at(parts, mu)[0]
-                upd = active & (Emu <= o.kappa_eps * mu) & (mu > mu_floor)
+                upd = active & ~resto & (Emu <= o.kappa_eps * mu) & (mu > mu_floor)
                 if not bool(upd.any()):
                     break
                 mu_new = torch.clamp(torch.minimum(o.kappa_mu * mu, mu ** o.theta_mu), min=mu_floor)
@@ -383,6 +419,21 @@ class InteriorPoint:
                 return torch.where(ft, start, grow)
 
             dxd, negd, rhs, Ss_reg = newton(None, delta_w, delta_c)
+            any_resto = bool((resto & active).any())
+            hess_in = ev['hess']
+            if any_resto:
+                # regularised Gauss-Newton step on the constraint violation (module docstring): primal barrier terms
+                rr = resto[:, None]
+                zeta = torch.sqrt(mu)[:, None]
+                SxR = mu_c * (iL * iL + iU * iU)
+                SsR = torch.where(ineq, mu_c * (jL * jL + jU * jU), torch.ones_like(s))
+                gbx = -mu_c * iL + mu_c * iU + o.kappa_d * mu_c * (dampL - dampU)
+                gbs = torch.where(ineq, -mu_c * jL + mu_c * jU + o.kappa_d * mu_c * (sdampL - sdampU), torch.zeros_like(s))
+                dxd = torch.where(rr, zeta * DR2 + SxR, dxd)
+                negd = torch.where(rr, torch.where(ineq, -(1.0 / o.resto_rho + 1.0 / SsR), torch.full_like(s, -1.0 / o.resto_rho)), negd)
+                rhs = torch.where(rr, torch.cat([-(zeta * DR2 * (x - x_R) + gbx),
+                                                 torch.where(ineq, -c - gbs / SsR, -c)], dim=1), rhs)
+                hess_in = torch.where(rr, torch.zeros_like(hess_in), hess_in)
             # Speculative candidates: a launch of the factorisation kernel takes as long for one instance as for a
             # full wave of them, so the spare slots of the last wave factorise the next `speculate` entries of
             # some instances' delta_w escalation sequences alongside; an instance whose first matrix has the wrong
@@ -405,13 +456,13 @@ class InteriorPoint:
                         spec_dw.append(dwc)
                         spec_parts.append(newton(spec_rows, dwc, delta_c[spec_rows]))
             if spec_rows is None:
-                sol, st = kkt(ev['hess'], ev['jac'], dxd, negd, rhs, active)
+                sol, st = kkt(hess_in, ev['jac'], dxd, negd, rhs, active)
             else:
                 t0 = time.perf_counter()
                 idx_act = torch.nonzero(active).squeeze(1)
                 idx_all = torch.cat([idx_act] + [spec_rows] * len(spec_parts))
                 cat = lambda k, full: torch.cat([full[idx_act]] + [p_[k] for p_ in spec_parts])
-                sol_all, st_all = be.kkt_solve_rows(ev['hess'], ev['jac'], idx_all, cat(0, dxd), cat(1, negd), cat(2, rhs),
+                sol_all, st_all = be.kkt_solve_rows(hess_in, ev['jac'], idx_all, cat(0, dxd), cat(1, negd), cat(2, rhs),
                                                     o.refine_steps)
                 if dev.type == 'cuda':
                     torch.cuda.synchronize(dev)
@@ -473,12 +524,19 @@ class InteriorPoint:
             dx = torch.where(mv, sol[:, :n], torch.zeros_like(x))
             dy = torch.where(mv, sol[:, n:], torch.zeros_like(y))
             ds = torch.where(mv & ineq, (dy - r_s) / Ss_reg, torch.zeros_like(s))
+            if any_resto:
+                rr = resto[:, None]
+                ds = torch.where(rr, torch.where(mv & ineq, (sol[:, n:] - gbs) / SsR, torch.zeros_like(s)), ds)
+                dy = torch.where(rr, torch.zeros_like(dy), dy)          # multipliers rest during restoration
             stalled = bad & (status == -1)
 
             dzL = (mu_c * iL - zL - zL * iL * dx) * fL
             dzU = (mu_c * iU - zU + zU * iU * dx) * fU
             dvL = (mu_c * jL - vL - vL * jL * ds) * sfL
             dvU = (mu_c * jU - vU + vU * jU * ds) * sfU
+            if any_resto:
+                keep_ = (~resto)[:, None].to(dt)
+                dzL, dzU, dvL, dvU = dzL * keep_, dzU * keep_, dvL * keep_, dvU * keep_
 
             def max_step(d_, step, f_, t_):
                 ''' largest alpha in (0, 1] with d_ + alpha * step >= (1 - tau) d_ '''
@@ -494,6 +552,12 @@ class InteriorPoint:
             theta = c.abs().sum(1)
             phi = barrier(ev['f'], x, s, mu)
             dphi = (gphi_x * dx).sum(1) + (gphi_s * ds).sum(1)
+            if any_resto:
+                # merit of the restoration problem and its slope along the step
+                zeta1 = torch.sqrt(mu)
+                phiR = 0.5 * o.resto_rho * (c * c).sum(1) + 0.5 * zeta1 * (DR2 * (x - x_R) ** 2).sum(1) + barrier(torch.zeros_like(mu), x, s, mu)
+                cJd = sol[:, n:] - o.resto_rho * c       # rho (J dx - ds) on inequality rows, rho J dx on equality rows: w = rho (c + Jc d)
+                dphiR = (c * cJd).sum(1) + (zeta1[:, None] * DR2 * (x - x_R) * dx).sum(1) + (gbx * dx).sum(1) + (gbs * ds).sum(1)
             alpha = a_pr.clone()
             searching = moved & (status == -1)
             accepted_alpha = torch.zeros_like(alpha)
@@ -540,6 +604,13 @@ class InteriorPoint:
                 armijo = ph_t <= ph0 + o.eta_phi * al * dph
                 suff = (th_t <= (1 - o.gamma_theta) * th0) | (ph_t <= ph0 - o.gamma_phi * th0)
                 ok = okfin & ~in_filter & (th_t <= theta_max[rows][:, None]) & torch.where(sw, armijo, suff)
+                if any_resto:
+                    c_t = torch.where(eq[rows][:, None, :], g_t - ceq[rows][:, None, :], g_t - st_)
+                    bar_t = ph_t - f_t                                                            # barrier terms only
+                    phR_t = 0.5 * o.resto_rho * (c_t * c_t).sum(2) + 0.5 * zeta1[rows][:, None] * (
+                        r_(DR2) * (xt - r_(x_R)) ** 2).sum(2) + bar_t
+                    okR = torch.isfinite(phR_t) & (phR_t <= phiR[rows][:, None] + 1e-4 * al * dphiR[rows][:, None])
+                    ok = torch.where(resto[rows][:, None], okR, ok)
                 # never accept a candidate beyond the max_ls-th halving
                 ok = ok & ((ls + torch.arange(Kw, device=dev)) < o.max_ls)[None, :]
                 any_ok = ok.any(1)
@@ -553,15 +624,37 @@ class InteriorPoint:
                 last_alpha[rej_rows] = al[~any_ok, Kw - 1]
                 alpha[rej_rows] = al[~any_ok, Kw - 1] * 0.5
                 ls += Kw
-            # failed searches: reset the filter and take the shortest trial step
             failed = searching
             if bool(failed.any()):
-                ls_fail = torch.where(failed, ls_fail + 1, ls_fail)
-                reset_filter(failed)
-                accepted_alpha = torch.where(failed, last_alpha, accepted_alpha)
+                # A failed search of the filter method far from feasibility starts the restoration at this point (no
+                # step now); a failed search inside the restoration ends the instance.  Close to feasibility (theta below
+                # theta_min, where the filter only asks for descent) the search usually fails on rounding noise: the
+                # filter is reset and the shortest trial step taken, three times in a row at most.
+                enter = failed & ~resto & (theta > theta_min) if o.restoration else torch.zeros_like(failed)
+                status[failed & resto] = 3
+                if bool(enter.any()):
+                    # the current point joins the filter, so that the method does not return here
+                    idx_f = torch.clamp(filt_n, max=F - 1)
+                    rows_e = torch.nonzero(enter).squeeze(1)
+                    filt_theta[rows_e, idx_f[rows_e]] = ((1 - o.gamma_theta) * theta)[rows_e]
+                    filt_phi[rows_e, idx_f[rows_e]] = (phi - o.gamma_phi * theta)[rows_e]
+                    filt_n[rows_e] = torch.clamp(filt_n[rows_e] + 1, max=F - 1)
+                    resto = resto | enter
+                    resto_it = torch.where(enter, torch.zeros_like(resto_it), resto_it)
+                    theta_R = torch.where(enter, theta, theta_R)
+                    x_R = torch.where(enter[:, None], x, x_R)
+                    DR2 = torch.where(enter[:, None], 1.0 / torch.clamp(x.abs(), min=1.0) ** 2, DR2)
+                    n_resto = n_resto + enter.long()
+                    res.n_restorations += int(enter.sum())
+                soft = failed & ~resto
+                ls_fail = torch.where(soft, ls_fail + 1, ls_fail)
+                reset_filter(soft)
+                accepted_alpha = torch.where(soft, last_alpha, accepted_alpha)
                 augment = augment & ~failed
-                status[failed & (ls_fail >= 3)] = 3
+                status[soft & (ls_fail >= 3)] = 3
             ls_fail = torch.where(moved & ~failed, torch.zeros_like(ls_fail), ls_fail)
+            was_resto = resto & moved & ~failed                   # took a restoration step in this sweep
+            augment = augment & ~resto
 
             # ---- filter augmentation, step, multiplier reset ----------------------------------------------
             if bool(augment.any()):
@@ -584,10 +677,15 @@ class InteriorPoint:
                 return torch.where(f_ > 0, torch.maximum(torch.minimum(z_, hi), lo), z_)
 
             zL, zU, vL, vU = reset(zL, dL, fL), reset(zU, dU, fU), reset(vL, eL, sfL), reset(vU, eU, sfU)
+            resto_it = resto_it + was_resto.long()
+            status[(resto_it >= o.resto_max_iter) & resto & (status == -1)] = 3
             iters = iters + moved.long()
             it += 1
             status[(status == -1) & (iters >= o.max_iter)] = 2
             active = status == -1
+            if o.verbose and any_resto and bool(resto[0] | was_resto[0]):
+                print(f'      [restoration] phi_R={float(phiR[0]):.6e} slope={float(dphiR[0]):.3e} theta_R={float(theta_R[0]):.3e} '
+                      f'it={int(resto_it[0])}')
             if o.verbose:
                 print(f'      alpha_pr={float(accepted_alpha[0]):.3e} a_max={float(a_pr[0]):.3e} alpha_du={float(a_du[0]):.3e} '
                       f'ls<={ls} failed={bool(failed[0])} theta={float(theta[0]):.3e} dphi={float(dphi[0]):.3e} '
@@ -630,7 +728,7 @@ class CudaBackend:
         self.vp = vp                                   # device tensor (nvp,) or (B, nvp)
         self._vp_full = vp
         self.K = kkt_solver or KktSolver(self.st)
-        self.refine_tol = 1e-13
+        self.refine_tol = 1e-10
         self._buf = {}
 
     def _out(self, name, shape, dev):

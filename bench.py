@@ -352,6 +352,7 @@ def run_solves(args, dev, rank, world, dist):
                         d2h_bytes_per_step=int(8 * B * (2 * st.nw + 2 * st.ng + 3))),
                warm_start_setup_s=t_build, gpu_launches=int(prod.functions.launch_count() - lib_launch0),
                speculative_factorisations=int(prod.solver.result.n_speculated),
+               restoration_visits=int(prod.solver.result.n_restorations),
                return_status_rank0={str(k): int(v) for k, v in zip(*np.unique(np.asarray(s['return_status']), return_counts=True))},
                workload='C5 shape: C2 x multi-start (w0_ws + 0.05*scale*N(0,1)) x vehicle parameters U[0.9,1.1]; '
                         'instance 0 of rank 0 is the nominal race.py problem')
@@ -463,7 +464,7 @@ def main():
     ap.add_argument('--no-colloc', action='store_true', help='skip the C1 (collocation) evaluation leg')
     ap.add_argument('--solves-batch', type=int, default=2048, help='multi-start instances per GPU in the solves leg')
     ap.add_argument('--solves-window', type=int, default=888, help='instances iterating at a time (continuous batching)')
-    ap.add_argument('--solves-refine', type=int, default=1, help='iterative-refinement steps per KKT solve')
+    ap.add_argument('--solves-refine', type=int, default=4, help='iterative-refinement steps per KKT solve')
     ap.add_argument('--solves-max-iter', type=int, default=300,
                     help='iteration cap per instance in the multi-start sweep (p99 of converged instances is ~280; '
                          'the reference sets 1000 for its single solves)')
