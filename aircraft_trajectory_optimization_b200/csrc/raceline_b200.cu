@@ -32,6 +32,7 @@
 #include "kkt_blocks.cuh"
 #include "kkt_big.cuh"
 #include "kkt_chain.cuh"
+#include "mesh_sdf.cuh"
 
 namespace {
 
@@ -643,6 +644,18 @@ int rb_nlp_hess_l(const rb_problem* p, int B, const double* x, const double* vp,
 int rb_nlp_eval_all(const rb_problem* p, int B, const double* x, const double* vp, const double* lam_f,
                     const double* lam_g, double* f, double* grad_f, double* g, double* jac, double* hess) {
   return host_eval(p, B, x, vp, lam_f, lam_g, f, grad_f, g, jac, hess);
+}
+
+// signed distance (positive outside) and closest point of np points to a triangle mesh; device pointers
+int rb_mesh_sdf(const double* tri, int nt, const double* pts, int np, double* dist, double* closest, void* stream) {
+  if (!tri || !pts || !dist) return fail("rb_mesh_sdf: null argument");
+  if (np <= 0) return 0;
+  if (nt <= 0) return fail("rb_mesh_sdf: empty mesh");
+  mesh_sdf_kernel<<<(unsigned)((np + RB_SDF_THREADS - 1) / RB_SDF_THREADS), RB_SDF_THREADS, 0,
+                    static_cast<cudaStream_t>(stream)>>>(tri, nt, pts, np, dist, closest);
+  g_launches++;
+  CK(cudaGetLastError());
+  return 0;
 }
 
 }  // extern "C"

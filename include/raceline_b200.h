@@ -215,6 +215,12 @@ int rb_kkt_resolve(const rb_kkt* k, int B, const double* hess, const double* jac
 int rb_kkt_matvec(const rb_kkt* k, int B, const double* hess, const double* jac, const double* dx_diag,
                   const double* neg_d, const double* vec, double* out, void* stream);
 
+/* Signed distance of np points to a triangle mesh, positive OUTSIDE (the convention of the reference's
+ * MeshObstacle.signed_distance, drone3d/obstacles/mesh_obstacle.py:38-42, which wraps trimesh.proximity), and the closest
+ * point on the mesh (optional, may be NULL) -- what the obstacle-free tube search needs (:110-145).
+ * tri [nt][9] vertex triples, pts [np][3], dist [np], closest [np][3]: DEVICE pointers. */
+int rb_mesh_sdf(const double* tri, int nt, const double* pts, int np, double* dist, double* closest, void* stream);
+
 /* instrumentation: when enabled, every rb_eval_batch brackets the interval-cell kernel (the dominant
  * kernel) with CUDA events on the launching stream; rb_profile_cell_ms waits for them, returns the
  * summed duration and the number of bracketed launches, and resets the counters. */
