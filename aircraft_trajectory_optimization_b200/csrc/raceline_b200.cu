@@ -33,6 +33,7 @@
 #include "kkt_big.cuh"
 #include "kkt_chain.cuh"
 #include "mesh_sdf.cuh"
+#include "ipm_glue.cuh"
 
 namespace {
 
@@ -653,6 +654,73 @@ int rb_mesh_sdf(const double* tri, int nt, const double* pts, int np, double* di
   if (nt <= 0) return fail("rb_mesh_sdf: empty mesh");
   mesh_sdf_kernel<<<(unsigned)((np + RB_SDF_THREADS - 1) / RB_SDF_THREADS), RB_SDF_THREADS, 0,
                     static_cast<cudaStream_t>(stream)>>>(tri, nt, pts, np, dist, closest);
+  g_launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ---- fused kernels of the interior-point sweep (csrc/ipm_glue.cuh); all pointers are device pointers -------------
+static_assert(sizeof(rb_ipm_args) == sizeof(RbIpm), "rb_ipm_args mirrors RbIpm");
+static RbIpm ipm_args(const rb_ipm_args* a) {
+  RbIpm r;
+  std::memcpy(&r, a, sizeof(RbIpm));
+  return r;
+}
+#define IPM_STREAM static_cast<cudaStream_t>(stream)
+int rb_ipm_error(const rb_ipm_args* a, double* out, void* stream) {
+  if (!a || !out) return fail("rb_ipm_error: null argument");
+  if (a->B <= 0) return 0;
+  ipm_error_kernel<<<a->B, RB_IPM_THREADS, 0, IPM_STREAM>>>(ipm_args(a), out);
+  g_launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+int rb_ipm_newton(const rb_ipm_args* a, const double* f, double* dxd, double* negd, double* rhs, double* gphi_x,
+                  double* gphi_s, double* c, double* r_s, double* Ssr, double* sc, void* stream) {
+  if (!a || !f || !dxd || !negd || !rhs || !gphi_x || !gphi_s || !c || !r_s || !Ssr || !sc) return fail("rb_ipm_newton: null argument");
+  if (a->B <= 0) return 0;
+  ipm_newton_kernel<<<a->B, RB_IPM_THREADS, 0, IPM_STREAM>>>(ipm_args(a), f, dxd, negd, rhs, gphi_x, gphi_s, c, r_s, Ssr, sc);
+  g_launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+int rb_ipm_direction(const rb_ipm_args* a, const double* sol, const unsigned char* moved, const double* tau,
+                     const double* gphi_x, const double* gphi_s, const double* c, const double* r_s, const double* Ssr,
+                     double* dx, double* dy, double* ds, double* dzL, double* dzU, double* dvL, double* dvU, double* sc,
+                     void* stream) {
+  if (!a || !sol || !moved || !tau || !dx || !dy || !ds || !dzL || !dzU || !dvL || !dvU || !sc) return fail("rb_ipm_direction: null argument");
+  if (a->B <= 0) return 0;
+  ipm_direction_kernel<<<a->B, RB_IPM_THREADS, 0, IPM_STREAM>>>(ipm_args(a), sol, moved, tau, gphi_x, gphi_s, c, r_s, Ssr, dx,
+                                                                 dy, ds, dzL, dzU, dvL, dvU, sc);
+  g_launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+int rb_ipm_trial(int n, int Kw, int ns, const int* rows, const double* al, const double* x, const double* dx, double* xt,
+                 void* stream) {
+  if (ns <= 0) return 0;
+  if (!rows || !al || !x || !dx || !xt) return fail("rb_ipm_trial: null argument");
+  ipm_trial_kernel<<<ns * Kw, RB_IPM_THREADS, 0, IPM_STREAM>>>(n, Kw, rows, al, x, dx, xt);
+  g_launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+int rb_ipm_trial_merit(const rb_ipm_args* a, int Kw, int ns, const int* rows, const double* al, const double* xt,
+                       const double* ds, const double* f_t, const double* g_t, double* out, void* stream) {
+  if (ns <= 0) return 0;
+  if (!a || !rows || !al || !xt || !ds || !f_t || !g_t || !out) return fail("rb_ipm_trial_merit: null argument");
+  ipm_trial_merit_kernel<<<ns * Kw, RB_IPM_THREADS, 0, IPM_STREAM>>>(ipm_args(a), Kw, rows, al, xt, ds, f_t, g_t, out);
+  g_launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+int rb_ipm_update(const rb_ipm_args* a, const double* alpha, const double* alpha_du, const double* dx, const double* dy,
+                  const double* ds, const double* dzL, const double* dzU, const double* dvL, const double* dvU,
+                  double kappa_sigma, void* stream) {
+  if (!a || !alpha || !alpha_du || !dx || !dy || !ds || !dzL || !dzU || !dvL || !dvU) return fail("rb_ipm_update: null argument");
+  if (a->B <= 0) return 0;
+  ipm_update_kernel<<<a->B, RB_IPM_THREADS, 0, IPM_STREAM>>>(ipm_args(a), alpha, alpha_du, dx, dy, ds, dzL, dzU, dvL, dvU,
+                                                              kappa_sigma);
   g_launches++;
   CK(cudaGetLastError());
   return 0;

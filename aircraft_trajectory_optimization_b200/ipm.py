@@ -82,6 +82,7 @@ class IpmOptions:
     compact_min: int = 16
     speculate: int = 2                 # spare slots of a factorisation wave try this many further delta_w candidates
     speculate_max: int = 4             # ... up to this many when the wave is mostly empty
+    use_glue: bool = True              # fused CUDA kernels for the vector work when the backend provides them
     restoration: bool = True           # feasibility restoration when the line search fails (see below)
     resto_kappa: float = 0.9           # leave restoration once theta <= resto_kappa * theta at entry
     resto_rho: float = 1e4             # weight of the constraint violation in the restoration merit (IPOPT: rho = 1000 on the l1 norm)
@@ -148,6 +149,13 @@ class InteriorPoint:
         sdampL, sdampU = (shasL & ~shasU).to(dt), (shasU & ~shasL).to(dt)
         fL, fU, sfL, sfU = hasL.to(dt), hasU.to(dt), shasL.to(dt), shasU.to(dt)
         n_bounds = (fL + fU).sum(1) + (sfL + sfU).sum(1)
+        # fused CUDA kernels for the vector work of a sweep (backend.glue; the torch arithmetic below is the same maths)
+        glue = getattr(be, 'glue', None) if o.use_glue else None
+        xflag = sflag = None
+        if glue is not None:
+            xflag = (hasL.to(torch.uint8) | (hasU.to(torch.uint8) << 1)).contiguous()
+            sflag = (shasL.to(torch.uint8) | (shasU.to(torch.uint8) << 1) | (eq.to(torch.uint8) << 2)).contiguous()
+            xL, xU, sL, sU, ceq = (t_.contiguous() for t_ in (xL, xU, sL, sU, ceq))
 
         def push(v, L, U, hL, hU):
             ''' move v strictly inside [L, U] (IPOPT bound_push / bound_frac) '''
@@ -241,6 +249,10 @@ class InteriorPoint:
             return dual, prim, s_d, s_c, prods
 
         def error_at(parts, mu_):
+            if parts[0] == 'glue':
+                _, dual, prim, s_d, s_c, pmin, pmax = parts
+                comp = torch.clamp(torch.maximum(pmax - mu_, mu_ - pmin), min=0.0)
+                return torch.stack([dual / s_d, prim, comp / s_c]).amax(0), dual, prim, comp
             dual, prim, s_d, s_c, prods = parts
             mc = mu_[:, None]
             comp = torch.stack([_inf_norm((pr - mc * f_)) for pr, f_ in zip(prods, (fL, fU, sfL, sfU))]).amax(0)
@@ -288,6 +300,12 @@ class InteriorPoint:
             filt_phi[mask, 0] = -float('inf')
             filt_n[mask] = 1
 
+        def GS():
+            ''' the current state tensors for the fused kernels (the names are re-bound as the sweep goes on) '''
+            return dict(x=x, s=s, y=y, zL=zL, zU=zU, vL=vL, vU=vU, xL=xL, xU=xU, sL=sL, sU=sU, ceq=ceq, xflag=xflag,
+                        sflag=sflag, mu=mu, delta_w=delta_w, delta_c=delta_c,
+                        resto=resto.to(torch.uint8) if bool(resto.any()) else None, x_R=x_R, DR2=DR2)
+
         # ---- physical compaction: once most instances have finished, the survivors are copied into smaller tensors so
         # that the elementwise work of a sweep scales with what is still iterating, not with the original batch
         B0 = B
@@ -330,6 +348,8 @@ class InteriorPoint:
                  moved_prev) = map(sel, (xL, xU, sL, sU, ceq, eq, ineq, fL, fU, sfL, sfU, dampL, dampU, sdampL, sdampU,
                                          n_bounds, lbx, ubx, moved_prev))
                 ev = {k_: sel(v_) for k_, v_ in ev.items()}
+                if glue is not None:
+                    xflag, sflag = sel(xflag), sel(sflag)
                 be.select(keep)
                 B = keep.numel()
                 active = status == -1
@@ -348,7 +368,16 @@ class InteriorPoint:
                     vL, vU = torch.where(lv, sfL, vL), torch.where(lv, sfU, vU)
                     ev = evaluate(x, y, True, leave, ev)                   # hess_l with the new multipliers
             # ---- convergence and barrier update --------------------------------------------------------
-            parts = error_parts(ev, x, s, y, zL, zU, vL, vU)
+            if glue is not None:
+                jty_cur = jt_y(ev['jac'], y).contiguous()
+                E8 = glue.error(GS(), ev, jty_cur)
+                n_tot = n + int(ineq[0].sum())
+                zsum_, ysum_ = E8[:, 2], E8[:, 3]
+                parts = ('glue', E8[:, 0], E8[:, 1],
+                         torch.clamp((ysum_ + zsum_) / max(1, m + n_tot), min=o.s_max) / o.s_max,
+                         torch.clamp(zsum_ / torch.clamp(n_bounds, min=1.0), min=o.s_max) / o.s_max, E8[:, 4], E8[:, 5])
+            else:
+                parts = error_parts(ev, x, s, y, zL, zU, vL, vU)
             E0, dual0, prim0, comp0 = error_at(parts, torch.zeros_like(mu))
             done = active & ~resto & (E0 <= o.tol)
             status[done] = 0
@@ -385,18 +414,25 @@ class InteriorPoint:
             tau = torch.clamp(1.0 - mu, min=o.tau_min)
 
             # ---- the Newton system ---------------------------------------------------------------------
-            dL, dU, eL, eU = slacks(x, s)
-            inv = lambda d_, f_: f_ / torch.where(f_ > 0, d_, torch.ones_like(d_))
-            iL, iU, jL, jU = inv(dL, fL), inv(dU, fU), inv(eL, sfL), inv(eU, sfU)
-            Sx = zL * iL + zU * iU
-            Ss = vL * jL + vU * jU
             mu_c = mu[:, None]
-            gphi_x = ev['grad_f'] - mu_c * iL + mu_c * iU + o.kappa_d * mu_c * (dampL - dampU)
-            gphi_s = torch.where(ineq, -mu_c * jL + mu_c * jU + o.kappa_d * mu_c * (sdampL - sdampU),
-                                 torch.zeros_like(s))
-            r_x = gphi_x + jt_y(ev['jac'], y)
-            r_s = torch.where(ineq, gphi_s - y, torch.zeros_like(s))
-            c = infeas(ev['g'], s)
+            if glue is not None:
+                x, s, y, zL, zU, vL, vU, mu, delta_w, delta_c = (t_.contiguous() for t_ in (x, s, y, zL, zU, vL, vU, mu,
+                                                                                            delta_w, delta_c))
+                NW = glue.newton(GS(), ev, jty_cur)
+                c, r_s, gphi_x, gphi_s = NW['c'], NW['r_s'], NW['gphi_x'], NW['gphi_s']
+                Sx = Ss = r_x = None
+            else:
+                dL, dU, eL, eU = slacks(x, s)
+                inv = lambda d_, f_: f_ / torch.where(f_ > 0, d_, torch.ones_like(d_))
+                iL, iU, jL, jU = inv(dL, fL), inv(dU, fU), inv(eL, sfL), inv(eU, sfU)
+                Sx = zL * iL + zU * iU
+                Ss = vL * jL + vU * jU
+                gphi_x = ev['grad_f'] - mu_c * iL + mu_c * iU + o.kappa_d * mu_c * (dampL - dampU)
+                gphi_s = torch.where(ineq, -mu_c * jL + mu_c * jU + o.kappa_d * mu_c * (sdampL - sdampU),
+                                     torch.zeros_like(s))
+                r_x = gphi_x + jt_y(ev['jac'], y)
+                r_s = torch.where(ineq, gphi_s - y, torch.zeros_like(s))
+                c = infeas(ev['g'], s)
 
             # One factorisation call per sweep (IPOPT's Algorithm IC, de-serialised over the batch): an instance
             # whose KKT matrix has the wrong inertia does not step in this sweep; it keeps its iterate, escalates
@@ -405,6 +441,15 @@ class InteriorPoint:
                 ''' (dx_diag, neg_d, rhs, Ss + dw) of the Newton system with regularisation (dw, dc); rows: index
                 tensor into the batch or None for every instance '''
                 pick = (lambda t: t) if rows is None else (lambda t: t[rows])
+                if glue is not None:
+                    # from the fused kernel's outputs (computed with the instance's current delta_w)
+                    if rows is None:
+                        return NW['dxd'], NW['negd'], NW['rhs'], NW['Ssr']
+                    iq, c_, dw0 = pick(ineq), pick(c), delta_w[rows][:, None]
+                    Ssr = torch.where(iq, pick(NW['Ssr']) - dw0 + dw[:, None], torch.ones_like(c_))
+                    negd_ = torch.where(iq, -1.0 / Ssr, torch.zeros_like(c_)) - dc[:, None]
+                    rhs_ = torch.cat([pick(NW['rhs'])[:, :n], torch.where(iq, -c_ - pick(r_s) / Ssr, -c_)], dim=1)
+                    return pick(NW['dxd']) - dw0 + dw[:, None], negd_, rhs_, Ssr
                 iq, Ss_, c_ = pick(ineq), pick(Ss), pick(c)
                 Ssr = torch.where(iq, Ss_ + dw[:, None], torch.ones_like(Ss_))
                 negd_ = torch.where(iq, -1.0 / Ssr, torch.zeros_like(Ss_)) - dc[:, None]
@@ -421,7 +466,9 @@ class InteriorPoint:
             dxd, negd, rhs, Ss_reg = newton(None, delta_w, delta_c)
             any_resto = bool((resto & active).any())
             hess_in = ev['hess']
-            if any_resto:
+            if any_resto and glue is not None:
+                hess_in = torch.where(resto[:, None], torch.zeros_like(hess_in), hess_in)      # W = 0 in the restoration
+            if any_resto and glue is None:
                 # regularised Gauss-Newton step on the constraint violation (module docstring): primal barrier terms
                 rr = resto[:, None]
                 zeta = torch.sqrt(mu)[:, None]
@@ -520,39 +567,49 @@ class InteriorPoint:
                 Ss_reg.index_copy_(0, rows_t, spec_parts[depth][3][spec_pos[rows_t]])
                 n_fact = n_fact + take.long()
                 pending = take
-            mv = moved[:, None]
-            dx = torch.where(mv, sol[:, :n], torch.zeros_like(x))
-            dy = torch.where(mv, sol[:, n:], torch.zeros_like(y))
-            ds = torch.where(mv & ineq, (dy - r_s) / Ss_reg, torch.zeros_like(s))
-            if any_resto:
-                rr = resto[:, None]
-                ds = torch.where(rr, torch.where(mv & ineq, (sol[:, n:] - gbs) / SsR, torch.zeros_like(s)), ds)
-                dy = torch.where(rr, torch.zeros_like(dy), dy)          # multipliers rest during restoration
             stalled = bad & (status == -1)
+            if glue is not None:
+                NW['Ssr'] = Ss_reg if Ss_reg.is_contiguous() else Ss_reg.contiguous()      # (rows of accepted speculative candidates differ)
+                DIR = glue.direction(GS(), sol.contiguous(), moved, tau.contiguous(), NW)
+                dx, dy, ds, dzL, dzU, dvL, dvU = (DIR[k_] for k_ in ('dx', 'dy', 'ds', 'dzL', 'dzU', 'dvL', 'dvU'))
+                a_pr, a_du = DIR['sc'][:, 0].clone(), DIR['sc'][:, 1].clone()
+            else:
+                mv = moved[:, None]
+                dx = torch.where(mv, sol[:, :n], torch.zeros_like(x))
+                dy = torch.where(mv, sol[:, n:], torch.zeros_like(y))
+                ds = torch.where(mv & ineq, (dy - r_s) / Ss_reg, torch.zeros_like(s))
+                if any_resto:
+                    rr = resto[:, None]
+                    ds = torch.where(rr, torch.where(mv & ineq, (sol[:, n:] - gbs) / SsR, torch.zeros_like(s)), ds)
+                    dy = torch.where(rr, torch.zeros_like(dy), dy)          # multipliers rest during restoration
 
-            dzL = (mu_c * iL - zL - zL * iL * dx) * fL
-            dzU = (mu_c * iU - zU + zU * iU * dx) * fU
-            dvL = (mu_c * jL - vL - vL * jL * ds) * sfL
-            dvU = (mu_c * jU - vU + vU * jU * ds) * sfU
-            if any_resto:
-                keep_ = (~resto)[:, None].to(dt)
-                dzL, dzU, dvL, dvU = dzL * keep_, dzU * keep_, dvL * keep_, dvU * keep_
+                dzL = (mu_c * iL - zL - zL * iL * dx) * fL
+                dzU = (mu_c * iU - zU + zU * iU * dx) * fU
+                dvL = (mu_c * jL - vL - vL * jL * ds) * sfL
+                dvU = (mu_c * jU - vU + vU * jU * ds) * sfU
+                if any_resto:
+                    keep_ = (~resto)[:, None].to(dt)
+                    dzL, dzU, dvL, dvU = dzL * keep_, dzU * keep_, dvL * keep_, dvU * keep_
 
-            def max_step(d_, step, f_, t_):
-                ''' largest alpha in (0, 1] with d_ + alpha * step >= (1 - tau) d_ '''
-                ratio = torch.where((step < 0) & (f_ > 0), -t_[:, None] * d_ / step, torch.full_like(d_, float('inf')))
-                return torch.clamp(ratio.amin(1), max=1.0) if ratio.shape[1] else torch.ones_like(t_)
+                def max_step(d_, step, f_, t_):
+                    ''' largest alpha in (0, 1] with d_ + alpha * step >= (1 - tau) d_ '''
+                    ratio = torch.where((step < 0) & (f_ > 0), -t_[:, None] * d_ / step, torch.full_like(d_, float('inf')))
+                    return torch.clamp(ratio.amin(1), max=1.0) if ratio.shape[1] else torch.ones_like(t_)
 
-            a_pr = torch.stack([max_step(dL, dx, fL, tau), max_step(dU, -dx, fU, tau),
-                                max_step(eL, ds, sfL, tau), max_step(eU, -ds, sfU, tau)]).amin(0)
-            a_du = torch.stack([max_step(zL, dzL, fL, tau), max_step(zU, dzU, fU, tau),
-                                max_step(vL, dvL, sfL, tau), max_step(vU, dvU, sfU, tau)]).amin(0)
+                a_pr = torch.stack([max_step(dL, dx, fL, tau), max_step(dU, -dx, fU, tau),
+                                    max_step(eL, ds, sfL, tau), max_step(eU, -ds, sfU, tau)]).amin(0)
+                a_du = torch.stack([max_step(zL, dzL, fL, tau), max_step(zU, dzU, fU, tau),
+                                    max_step(vL, dvL, sfL, tau), max_step(vU, dvU, sfU, tau)]).amin(0)
 
             # ---- filter line search ---------------------------------------------------------------------
-            theta = c.abs().sum(1)
-            phi = barrier(ev['f'], x, s, mu)
-            dphi = (gphi_x * dx).sum(1) + (gphi_s * ds).sum(1)
-            if any_resto:
+            if glue is not None:
+                theta, phi, phiR = NW['sc'][:, 0].clone(), NW['sc'][:, 1].clone(), NW['sc'][:, 2].clone()
+                dphi, dphiR = DIR['sc'][:, 2].clone(), DIR['sc'][:, 3].clone()
+            else:
+                theta = c.abs().sum(1)
+                phi = barrier(ev['f'], x, s, mu)
+                dphi = (gphi_x * dx).sum(1) + (gphi_s * ds).sum(1)
+            if any_resto and glue is None:
                 # merit of the restoration problem and its slope along the step
                 zeta1 = torch.sqrt(mu)
                 phiR = 0.5 * o.resto_rho * (c * c).sum(1) + 0.5 * zeta1 * (DR2 * (x - x_R) ** 2).sum(1) + barrier(torch.zeros_like(mu), x, s, mu)
@@ -576,26 +633,38 @@ class InteriorPoint:
                     break
                 ns = rows.numel()
                 al = alpha[rows][:, None] * halves[None, :]                                    # [ns, Kw]
-                xt = x[rows][:, None, :] + al[:, :, None] * dx[rows][:, None, :]               # [ns, Kw, n]
-                st_ = torch.where(ineq[rows][:, None, :], s[rows][:, None, :] + al[:, :, None] * ds[rows][:, None, :],
-                                  ceq[rows][:, None, :])
-                t0 = time.perf_counter()
-                evt = be.eval_points(xt.reshape(ns * Kw, n), rows.repeat_interleave(Kw))
-                if dev.type == 'cuda':
-                    torch.cuda.synchronize(dev)
-                res.t_eval += time.perf_counter() - t0
-                res.n_eval += 1
-                g_t, f_t = evt['g'].reshape(ns, Kw, m), evt['f'].reshape(ns, Kw)
-                th_t = torch.where(eq[rows][:, None, :], g_t - ceq[rows][:, None, :], g_t - st_).abs().sum(2)
-                # barrier function at the trial points
-                lg = lambda d_, f_: (torch.log(torch.where(f_ > 0, d_, torch.ones_like(d_))) * f_).sum(2)
-                r_ = lambda t: t[rows][:, None, :]
-                dLt, dUt, eLt, eUt = xt - r_(xL), r_(xU) - xt, st_ - r_(sL), r_(sU) - st_
-                mu_r = mu[rows][:, None]
-                ph_t = f_t - mu_r * (lg(dLt, r_(fL)) + lg(dUt, r_(fU)) + lg(eLt, r_(sfL)) + lg(eUt, r_(sfU)))
-                ph_t = ph_t + o.kappa_d * mu_r * ((dLt * r_(dampL)).sum(2) + (dUt * r_(dampU)).sum(2)
-                                                  + (eLt * r_(sdampL)).sum(2) + (eUt * r_(sdampU)).sum(2))
-                okfin = torch.isfinite(th_t) & torch.isfinite(ph_t)
+                if glue is not None:
+                    al = al.contiguous()
+                    xt2, rows32 = glue.trial(x, dx, rows, al)                                  # [ns * Kw, n]
+                    t0 = time.perf_counter()
+                    evt = be.eval_points(xt2, rows.repeat_interleave(Kw))
+                    if dev.type == 'cuda':
+                        torch.cuda.synchronize(dev)
+                    res.t_eval += time.perf_counter() - t0
+                    res.n_eval += 1
+                    TM = glue.trial_merit(GS(), rows32, al, xt2, ds, evt['f'].contiguous(), evt['g'].contiguous())
+                    th_t, ph_t, phR_t, okfin = TM[:, :, 0], TM[:, :, 1], TM[:, :, 2], TM[:, :, 3] > 0.5
+                else:
+                    xt = x[rows][:, None, :] + al[:, :, None] * dx[rows][:, None, :]               # [ns, Kw, n]
+                    st_ = torch.where(ineq[rows][:, None, :], s[rows][:, None, :] + al[:, :, None] * ds[rows][:, None, :],
+                                      ceq[rows][:, None, :])
+                    t0 = time.perf_counter()
+                    evt = be.eval_points(xt.reshape(ns * Kw, n), rows.repeat_interleave(Kw))
+                    if dev.type == 'cuda':
+                        torch.cuda.synchronize(dev)
+                    res.t_eval += time.perf_counter() - t0
+                    res.n_eval += 1
+                    g_t, f_t = evt['g'].reshape(ns, Kw, m), evt['f'].reshape(ns, Kw)
+                    th_t = torch.where(eq[rows][:, None, :], g_t - ceq[rows][:, None, :], g_t - st_).abs().sum(2)
+                    # barrier function at the trial points
+                    lg = lambda d_, f_: (torch.log(torch.where(f_ > 0, d_, torch.ones_like(d_))) * f_).sum(2)
+                    r_ = lambda t: t[rows][:, None, :]
+                    dLt, dUt, eLt, eUt = xt - r_(xL), r_(xU) - xt, st_ - r_(sL), r_(sU) - st_
+                    mu_r = mu[rows][:, None]
+                    ph_t = f_t - mu_r * (lg(dLt, r_(fL)) + lg(dUt, r_(fU)) + lg(eLt, r_(sfL)) + lg(eUt, r_(sfU)))
+                    ph_t = ph_t + o.kappa_d * mu_r * ((dLt * r_(dampL)).sum(2) + (dUt * r_(dampU)).sum(2)
+                                                      + (eLt * r_(sdampL)).sum(2) + (eUt * r_(sdampU)).sum(2))
+                    okfin = torch.isfinite(th_t) & torch.isfinite(ph_t)
                 ft, fp = filt_theta[rows][:, None, :], filt_phi[rows][:, None, :]
                 in_filter = ((th_t[:, :, None] >= (1 - o.gamma_theta) * ft)
                              & (ph_t[:, :, None] >= fp - o.gamma_phi * ft)).any(2)
@@ -605,10 +674,11 @@ class InteriorPoint:
                 suff = (th_t <= (1 - o.gamma_theta) * th0) | (ph_t <= ph0 - o.gamma_phi * th0)
                 ok = okfin & ~in_filter & (th_t <= theta_max[rows][:, None]) & torch.where(sw, armijo, suff)
                 if any_resto:
-                    c_t = torch.where(eq[rows][:, None, :], g_t - ceq[rows][:, None, :], g_t - st_)
-                    bar_t = ph_t - f_t                                                            # barrier terms only
-                    phR_t = 0.5 * o.resto_rho * (c_t * c_t).sum(2) + 0.5 * zeta1[rows][:, None] * (
-                        r_(DR2) * (xt - r_(x_R)) ** 2).sum(2) + bar_t
+                    if glue is None:
+                        c_t = torch.where(eq[rows][:, None, :], g_t - ceq[rows][:, None, :], g_t - st_)
+                        bar_t = ph_t - f_t                                                        # barrier terms only
+                        phR_t = 0.5 * o.resto_rho * (c_t * c_t).sum(2) + 0.5 * zeta1[rows][:, None] * (
+                            r_(DR2) * (xt - r_(x_R)) ** 2).sum(2) + bar_t
                     okR = torch.isfinite(phR_t) & (phR_t <= phiR[rows][:, None] + 1e-4 * al * dphiR[rows][:, None])
                     ok = torch.where(resto[rows][:, None], okR, ok)
                 # never accept a candidate beyond the max_ls-th halving
@@ -663,20 +733,24 @@ class InteriorPoint:
                 filt_theta[rows, idx[rows]] = ((1 - o.gamma_theta) * theta)[rows]
                 filt_phi[rows, idx[rows]] = (phi - o.gamma_phi * theta)[rows]
                 filt_n[rows] = torch.clamp(filt_n[rows] + 1, max=F - 1)
-            a = accepted_alpha[:, None]
-            x = x + a * dx
-            s = torch.where(ineq, s + a * ds, ceq)
-            y = y + a * dy
-            ad = (a_du * moved)[:, None]
-            zL, zU, vL, vU = zL + ad * dzL, zU + ad * dzU, vL + ad * dvL, vU + ad * dvU
-            dL, dU, eL, eU = slacks(x, s)
+            if glue is not None:
+                # (x_R is a separate tensor: the in-place update of x does not touch the restoration reference)
+                glue.update(GS(), accepted_alpha.contiguous(), (a_du * moved).contiguous(), DIR, o.kappa_sigma)
+            else:
+                a = accepted_alpha[:, None]
+                x = x + a * dx
+                s = torch.where(ineq, s + a * ds, ceq)
+                y = y + a * dy
+                ad = (a_du * moved)[:, None]
+                zL, zU, vL, vU = zL + ad * dzL, zU + ad * dzU, vL + ad * dvL, vU + ad * dvU
+                dL, dU, eL, eU = slacks(x, s)
 
-            def reset(z_, d_, f_):
-                d_ = torch.where(f_ > 0, d_, torch.ones_like(d_))
-                lo, hi = mu_c / (o.kappa_sigma * d_), o.kappa_sigma * mu_c / d_
-                return torch.where(f_ > 0, torch.maximum(torch.minimum(z_, hi), lo), z_)
+                def reset(z_, d_, f_):
+                    d_ = torch.where(f_ > 0, d_, torch.ones_like(d_))
+                    lo, hi = mu_c / (o.kappa_sigma * d_), o.kappa_sigma * mu_c / d_
+                    return torch.where(f_ > 0, torch.maximum(torch.minimum(z_, hi), lo), z_)
 
-            zL, zU, vL, vU = reset(zL, dL, fL), reset(zU, dU, fU), reset(vL, eL, sfL), reset(vU, eU, sfU)
+                zL, zU, vL, vU = reset(zL, dL, fL), reset(zU, dU, fU), reset(vL, eL, sfL), reset(vU, eU, sfU)
             resto_it = resto_it + was_resto.long()
             status[(resto_it >= o.resto_max_iter) & resto & (status == -1)] = 3
             iters = iters + moved.long()
@@ -730,6 +804,16 @@ class CudaBackend:
         self.K = kkt_solver or KktSolver(self.st)
         self.refine_tol = 1e-10
         self._buf = {}
+        self._glue = None
+
+    @property
+    def glue(self):
+        ''' fused kernels for the vector work of the interior-point sweep (glue.py) '''
+        if self._glue is None:
+            from .glue import IpmGlue
+            d = IpmOptions()
+            self._glue = IpmGlue(d.kappa_d, d.resto_rho)
+        return self._glue
 
     def _out(self, name, shape, dev):
         t = self._buf.get(name)

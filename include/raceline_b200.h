@@ -215,6 +215,48 @@ int rb_kkt_resolve(const rb_kkt* k, int B, const double* hess, const double* jac
 int rb_kkt_matvec(const rb_kkt* k, int B, const double* hess, const double* jac, const double* dx_diag,
                   const double* neg_d, const double* vec, double* out, void* stream);
 
+/* ---- fused vector kernels of the interior-point sweep ("K3" of SURVEY.md s2.1) ---------------------------------------
+ * They replace the per-iteration vector work IPOPT does around its linear solves inside `self.solver(x0=...)`
+ * (drone3d/raceline/base_raceline.py:160-165): optimality error, condensed KKT right-hand side, fraction-to-the-boundary
+ * rule, trial points and their filter quantities, primal-dual update.  B instances, n variables, m constraint rows;
+ * all pointers are DEVICE pointers; state vectors are [B][n] / [B][m].  Bounds and flags have row strides sx / ss (0: one
+ * row shared by all instances).  xflag bit0 lower bound, bit1 upper bound; sflag bit0 / bit1 the same for the slack of an
+ * inequality row, bit2 equality row.  resto / x_R / DR2 may be NULL (no instance in feasibility restoration). */
+typedef struct rb_ipm_args {
+  int B, n, m;
+  long long sx, ss;
+  const double *xL, *xU, *sL, *sU, *ceq;
+  const unsigned char *xflag, *sflag;
+  double *x, *s, *y, *zL, *zU, *vL, *vU;
+  const double *grad_f, *g, *jty;
+  const double *mu, *delta_w, *delta_c;
+  const unsigned char* resto;
+  const double *x_R, *DR2;
+  double kappa_d, rho;
+} rb_ipm_args;
+/* out [B][8]: |grad L|_inf, |c|_inf, sum of bound multipliers, |y|_1, min / max complementarity product, |c|_1, 0 */
+int rb_ipm_error(const rb_ipm_args* a, double* out, void* stream);
+/* dxd [B][n], negd [B][m], rhs [B][n+m] of the condensed Newton system; gphi_x, gphi_s, c, r_s, Ssr are kept for
+ * rb_ipm_direction; sc [B][4]: theta, barrier objective (needs f [B]), restoration merit, 0 */
+int rb_ipm_newton(const rb_ipm_args* a, const double* f, double* dxd, double* negd, double* rhs, double* gphi_x,
+                  double* gphi_s, double* c, double* r_s, double* Ssr, double* sc, void* stream);
+/* search direction from the KKT solution sol [B][n+m]; sc [B][4]: alpha_pr_max, alpha_du_max, slope of the barrier
+ * objective, slope of the restoration merit */
+int rb_ipm_direction(const rb_ipm_args* a, const double* sol, const unsigned char* moved, const double* tau,
+                     const double* gphi_x, const double* gphi_s, const double* c, const double* r_s, const double* Ssr,
+                     double* dx, double* dy, double* ds, double* dzL, double* dzU, double* dvL, double* dvU, double* sc,
+                     void* stream);
+/* xt [ns][Kw][n] = x[rows[r]] + al[r][k] dx[rows[r]] */
+int rb_ipm_trial(int n, int Kw, int ns, const int* rows, const double* al, const double* x, const double* dx, double* xt,
+                 void* stream);
+/* out [ns*Kw][4]: theta, barrier objective, restoration merit, finite flag at the trial points (f_t, g_t evaluated there) */
+int rb_ipm_trial_merit(const rb_ipm_args* a, int Kw, int ns, const int* rows, const double* al, const double* xt,
+                       const double* ds, const double* f_t, const double* g_t, double* out, void* stream);
+/* x, s, y, z, v updated in place with the accepted step lengths; multipliers kept within kappa_sigma of mu / slack */
+int rb_ipm_update(const rb_ipm_args* a, const double* alpha, const double* alpha_du, const double* dx, const double* dy,
+                  const double* ds, const double* dzL, const double* dzU, const double* dvL, const double* dvU,
+                  double kappa_sigma, void* stream);
+
 /* Signed distance of np points to a triangle mesh, positive OUTSIDE (the convention of the reference's
  * MeshObstacle.signed_distance, drone3d/obstacles/mesh_obstacle.py:38-42, which wraps trimesh.proximity), and the closest
  * point on the mesh (optional, may be NULL) -- what the obstacle-free tube search needs (:110-145).

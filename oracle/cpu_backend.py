@@ -83,7 +83,10 @@ class OracleBackend:
                 try:
                     x, neg = block_solve(*args, r, with_inertia=True)
                     for _ in range(refine_steps):
-                        x = x + block_solve(*args, r - K @ x)
+                        rr = r - K @ x
+                        if np.abs(rr).max() <= 1e-10 * max(1.0, np.abs(r).max()):      # like CudaBackend.refine_tol
+                            break
+                        x = x + block_solve(*args, rr)
                     sol[b], status[b, 1] = x, neg
                 except np.linalg.LinAlgError:
                     sol[b] = np.nan
@@ -93,7 +96,10 @@ class OracleBackend:
                 lu = spla.splu(K.tocsc())
                 x = lu.solve(r)
                 for _ in range(refine_steps):
-                    x = x + lu.solve(r - K @ x)
+                    rr = r - K @ x
+                    if np.abs(rr).max() <= 1e-10 * max(1.0, np.abs(r).max()):
+                        break
+                    x = x + lu.solve(rr)
                 sol[b] = x
                 if self.check_inertia:
                     import scipy.linalg as sla
