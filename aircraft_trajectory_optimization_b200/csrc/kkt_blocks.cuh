@@ -55,12 +55,13 @@ struct RbKktBatch {
 
 struct KktVals {
   const double *hess, *jac, *dx, *nd;
+  const double* aux;      // source kind 4: values of a condensed system (kkt_condense.cuh), else unused
 };
 
 __device__ __forceinline__ double kkt_val(const KktVals& v, int32_t src) {
-  const int kind = (src >> 28) & 3;
+  const int kind = (src >> 28) & 7;
   const int idx = src & 0x0fffffff;
-  const double* base = kind == 0 ? v.hess : (kind == 1 ? v.jac : (kind == 2 ? v.dx : v.nd));
+  const double* base = kind == 0 ? v.hess : (kind == 1 ? v.jac : (kind == 2 ? v.dx : (kind == 3 ? v.nd : v.aux)));
   return base[idx];
 }
 

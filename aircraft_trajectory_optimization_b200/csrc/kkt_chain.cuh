@@ -76,6 +76,10 @@ struct RbKktChainBatch {
   int* status;                                  // [B][2] vanishing pivots, negative eigenvalues
   int pq_stage;                                 // doubles of the P part of a TMA stage buffer (solve kernel)
   RbKktRecDev rt;
+  // condensed systems (kkt_condense.cuh): values of source kind 4, [B][naux]; pivot counts of the interiors to add
+  const double* aux;
+  int naux;
+  const int* status_add;                        // [B][2] or null
 };
 
 __device__ __forceinline__ double kf_upd1(double m, double c, double r) { return __fma_rn(-c, r, m); }
@@ -451,9 +455,9 @@ __device__ __forceinline__ void kf_cp_wait() {
 }
 
 __device__ __forceinline__ const double* kkt_val_ptr(const KktVals& v, int32_t src) {
-  const int kind = (src >> 28) & 3;
+  const int kind = (src >> 28) & 7;
   const int idx = src & 0x0fffffff;
-  const double* base = kind == 0 ? v.hess : (kind == 1 ? v.jac : (kind == 2 ? v.dx : v.nd));
+  const double* base = kind == 0 ? v.hess : (kind == 1 ? v.jac : (kind == 2 ? v.dx : (kind == 3 ? v.nd : v.aux)));
   return base + idx;
 }
 
@@ -487,7 +491,7 @@ kkt_factor_kernel(const RbKktDev d, const RbKktChainBatch bt) {
     s.stat = reinterpret_cast<int*>(s.vec + 2);
   }
   KktVals v{bt.hess + (size_t)p * bt.nnzh, bt.jac + (size_t)p * bt.nnzj, bt.dx_diag + (size_t)p * d.nw,
-            bt.neg_d + (size_t)p * d.ng};
+            bt.neg_d + (size_t)p * d.ng, bt.aux ? bt.aux + (size_t)p * bt.naux : nullptr};
   double* __restrict__ Sinv_g = bt.Sinv + (size_t)p * N * bmax * d.ldS;
   double* __restrict__ YL_g = bt.YL + (size_t)p * N * bmax * d.ldY;
   double* __restrict__ P_g = bt.P + (size_t)p * bt.p_total;
@@ -741,8 +745,8 @@ kkt_factor_kernel(const RbKktDev d, const RbKktChainBatch bt) {
   }
   __syncthreads();
   if (tid == 0 && bt.status) {
-    bt.status[2 * p] = s.stat[0];
-    bt.status[2 * p + 1] = s.stat[1];
+    bt.status[2 * p] = s.stat[0] + (bt.status_add ? bt.status_add[2 * p] : 0);
+    bt.status[2 * p + 1] = s.stat[1] + (bt.status_add ? bt.status_add[2 * p + 1] : 0);
   }
 }
 

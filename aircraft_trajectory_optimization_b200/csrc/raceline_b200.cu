@@ -32,6 +32,7 @@
 #include "kkt_blocks.cuh"
 #include "kkt_big.cuh"
 #include "kkt_chain.cuh"
+#include "kkt_condense.cuh"
 #include "mesh_sdf.cuh"
 #include "ipm_glue.cuh"
 

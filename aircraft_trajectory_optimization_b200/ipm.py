@@ -882,6 +882,9 @@ class CudaBackend:
         ''' instances one launch of the factorisation kernel holds at once (CTAs per SM x SMs): a launch with fewer
         instances takes as long, so the driver fills the spare slots with speculative regularisation candidates '''
         sms = torch.cuda.get_device_properties(self.vp.device).multi_processor_count
+        if getattr(self.K, 'cs', None) is not None:
+            # condensed collocation intervals: the interior kernel runs one CTA per (interval, instance), one CTA per SM
+            return max(1, sms // self.K.cs.NI)
         return sms * (3 if self.K.ks.bmax <= 64 else 1)
 
     def kkt_solve_rows(self, hess, jac, idx, dx_diag, neg_d, rhs, refine_steps):

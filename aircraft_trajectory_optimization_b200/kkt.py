@@ -135,8 +135,17 @@ def _var_stage(st):
     return t, is_node
 
 
-def build_kkt_structure(st) -> KKTStructure:
-    ''' st: NLPStructure (structure.py) '''
+def _pattern(st):
+    ''' (row, column) of every jac_g / hess_l entry '''
+    jr = np.asarray(st.jac_row, dtype=np.int64)
+    jc = np.repeat(np.arange(st.nw), np.diff(st.jac_colind))
+    hr = np.asarray(st.hess_row, dtype=np.int64)
+    hc = np.repeat(np.arange(st.nw), np.diff(st.hess_colind))
+    return jr, jc, hr, hc
+
+
+def _assign_blocks(st):
+    ''' chain block (0 .. N-1 in sweep order, N = border) of every KKT unknown.  Returns (blk, N). '''
     nw, ng, N = st.nw, st.ng, st.N
     t, is_node = _var_stage(st)
     jr = np.asarray(st.jac_row, dtype=np.int64)
@@ -229,11 +238,28 @@ def build_kkt_structure(st) -> KKTStructure:
     demoted += list(np.nonzero(eq_row & (blk[nw:] < N) & ~has_own)[0])
     if demoted:
         blk[nw + np.array(demoted, dtype=np.int64)] = N
+    return blk, N
 
+
+def build_kkt_structure(st) -> KKTStructure:
+    ''' st: NLPStructure (structure.py) '''
+    blk, N = _assign_blocks(st)
+    jr, jc, hr, hc = _pattern(st)
+    ei = np.concatenate([hr, st.nw + jr])
+    ej = np.concatenate([hc, jc])
+    es = np.concatenate([src_code(K_HESS, np.arange(len(hr))), src_code(K_JAC, np.arange(len(jr)))])
+    return _tables_from_blocks(st.nw, st.ng, N, blk, ei, ej, es)
+
+
+def _tables_from_blocks(nw, ng, N, blk, ei, ej, es) -> KKTStructure:
+    '''
+    block tables of the symmetric matrix with entries (ei, ej, src es), every unordered pair listed once, whose
+    unknowns are grouped by blk: 0 .. N-1 chain blocks (entries only inside a block or between neighbours), N the
+    border, N + 1 unknowns that do not take part (eliminated beforehand: kkt_condensed.py)
+    '''
     # local order inside a block: variables (ascending w index) then rows (ascending g index); border unknowns by the
     # first chain block they couple to (unknowns that only couple inside the border last)
-    ei0 = np.concatenate([hr, nw + jr])
-    ej0 = np.concatenate([hc, jc])
+    ei0, ej0 = ei, ej
     first = np.zeros(nw + ng, dtype=np.int64)
     fb = np.full(nw + ng, N, dtype=np.int64)
     m_i = (blk[ei0] == N) & (blk[ej0] < N)
@@ -243,18 +269,15 @@ def build_kkt_structure(st) -> KKTStructure:
     first[blk == N] = fb[blk == N]
     order = np.lexsort((np.arange(nw + ng), first, blk))
     unk = order.astype(np.int32)
-    counts = np.bincount(blk, minlength=N + 1)
+    counts = np.bincount(blk, minlength=N + 2)[:N + 1]
     blk_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
     loc = np.empty(nw + ng, dtype=np.int64)
     loc[order] = np.arange(nw + ng) - blk_ptr[blk[order]]
-    nvar = np.bincount(blk[:nw], minlength=N + 1).astype(np.int32)
+    nvar = np.bincount(blk[:nw], minlength=N + 2)[:N + 1].astype(np.int32)
     bmax = int(counts[:N].max())
     nb = int(counts[N])
 
     # ---- all KKT entries (i, j, src) in the lower+upper sense: list each unordered pair once ------
-    ei = np.concatenate([hr, nw + jr])
-    ej = np.concatenate([hc, jc])
-    es = np.concatenate([src_code(K_HESS, np.arange(len(hr))), src_code(K_JAC, np.arange(len(jr)))])
     bi, bj = blk[ei], blk[ej]
     li, lj = loc[ei], loc[ej]
 
@@ -368,8 +391,16 @@ class _KktDesc(ctypes.Structure):
                 + [(k, _i64p) for k in ('jac_colind', 'jac_row', 'hess_colind', 'hess_row')])
 
 
+class _KktInteriorDesc(ctypes.Structure):
+    _fields_ = ([(k, ctypes.c_int) for k in ('NI', 'amax', 'smax', 'n_aux', 'n_rsep')]
+                + [(k, _i32p) for k in ('iu_ptr', 'iunk', 'su_ptr', 'sunk', 'iA_ptr', 'iA_pos', 'iA_src', 'iB_ptr',
+                                        'iB_pos', 'iB_src', 'aux_orig', 'aux_c_ptr', 'aux_c_idx', 'rsep', 'r_c_ptr',
+                                        'r_c_idx')])
+
+
 def bind_kkt(lib):
     vp = ctypes.c_void_p
+    lib.rb_kkt_set_interiors.argtypes = [vp, ctypes.POINTER(_KktInteriorDesc)]
     lib.rb_kkt_create.argtypes = [ctypes.POINTER(_KktDesc), ctypes.POINTER(vp)]
     lib.rb_kkt_destroy.argtypes = [vp]
     lib.rb_kkt_destroy.restype = None
@@ -386,12 +417,23 @@ class KktSolver:
     fp64 tensors (contiguous); see include/raceline_b200.h for shapes.
     '''
 
-    def __init__(self, st, ks: KKTStructure = None):
+    def __init__(self, st, ks: KKTStructure = None, condensed=None):
+        '''
+        condensed: eliminate the interiors of collocation intervals first (kkt_condensed.py); default: whenever the
+        transcription has interior collocation points (K > 0).  `ks` then is the structure of the reduced system.
+        '''
         from .functions import load_library, _check
         self._check = _check
         self.lib = load_library()
         bind_kkt(self.lib)
         self.st = st
+        if condensed is None:
+            condensed = ks is None and st.K > 0
+        self.cs = None
+        if condensed:
+            from .kkt_condensed import build_condensed_structure
+            self.cs = build_condensed_structure(st)
+            ks = self.cs.chain
         self.ks = ks or build_kkt_structure(st)
         ks = self.ks
         self._keep = []
@@ -411,6 +453,15 @@ class KktSolver:
             setattr(d, name, a.ctypes.data_as(_i64p))
         self.handle = ctypes.c_void_p()
         _check(self.lib.rb_kkt_create(ctypes.byref(d), ctypes.byref(self.handle)), 'rb_kkt_create')
+        if self.cs is not None:
+            cs = self.cs
+            di = _KktInteriorDesc()
+            di.NI, di.amax, di.smax, di.n_aux, di.n_rsep = cs.NI, cs.amax, cs.smax, cs.n_aux, len(cs.rsep)
+            for name, arr in cs.tables().items():
+                a = np.ascontiguousarray(arr, dtype=np.int32)
+                self._keep.append(a)
+                setattr(di, name, a.ctypes.data_as(_i32p))
+            _check(self.lib.rb_kkt_set_interiors(self.handle, ctypes.byref(di)), 'rb_kkt_set_interiors')
         self._factors = None
         self._factors_B = 0
 

@@ -200,6 +200,20 @@ typedef struct rb_kkt_desc {
 
 int rb_kkt_create(const rb_kkt_desc* desc, rb_kkt** out);
 void rb_kkt_destroy(rb_kkt* k);
+
+/* Collocation transcriptions (drone3d/raceline/base_raceline.py:398-490, K = 7 points per interval): the interior
+ * unknowns of every interval are eliminated first, all intervals at once, and `desc` of rb_kkt_create then describes the
+ * reduced (multiple-shooting-shaped) system whose values come from the aux array (source kind 4).  Tables:
+ * aircraft_trajectory_optimization_b200/kkt_condensed.py.  Call once, right after rb_kkt_create. */
+typedef struct rb_kkt_interior_desc {
+  int NI, amax, smax, n_aux, n_rsep;
+  const int32_t *iu_ptr, *iunk, *su_ptr, *sunk;            /* interior / touched separator unknowns per interval */
+  const int32_t *iA_ptr, *iA_pos, *iA_src;                 /* A_n entries */
+  const int32_t *iB_ptr, *iB_pos, *iB_src;                 /* B_n entries */
+  const int32_t *aux_orig, *aux_c_ptr, *aux_c_idx;         /* reduced-system values: original source + T_n entries */
+  const int32_t *rsep, *r_c_ptr, *r_c_idx;                 /* reduced right-hand side */
+} rb_kkt_interior_desc;
+int rb_kkt_set_interiors(rb_kkt* k, const rb_kkt_interior_desc* desc);
 /* bytes of factor storage (block inverses, coupling solves, border columns) for a batch of B */
 size_t rb_kkt_factor_bytes(const rb_kkt* k, int B);
 /* factor K and solve K sol = rhs for B instances.  hess [B][nnz_hess], jac [B][nnz_jac], dx_diag [B][nw],

@@ -27,13 +27,14 @@ def sparse_solve(st, hess, jac, dx_diag, D, rhs):
     return spla.splu(K).solve(rhs)
 
 
-def _gather(ks, src, hess, jac, dx_diag, neg_d):
+def _gather(ks, src, hess, jac, dx_diag, neg_d, aux=None):
     kind = src >> 28
     idx = src & ((1 << 28) - 1)
     out = np.empty(len(src))
-    for k, arr in enumerate((hess, jac, dx_diag, neg_d)):
+    for k, arr in enumerate((hess, jac, dx_diag, neg_d, aux)):
         m = kind == k
-        out[m] = arr[idx[m]]
+        if m.any():
+            out[m] = arr[idx[m]]
     return out
 
 
@@ -169,7 +170,7 @@ def block_solve(ks, hess, jac, dx_diag, D, rhs, with_inertia=False):
     return (sol, neg) if with_inertia else sol
 
 
-def chain_factor(ks, hess, jac, dx_diag, D):
+def chain_factor(ks, hess, jac, dx_diag, D, aux=None):
     '''
     numpy twin of kkt_factor_kernel (csrc/kkt_chain.cuh): block LDL' of the chain with the border last.  The border
     columns are carried in interface form: Y_n = (L^-1 E)_n lives on the support rows sup_n of block n only,
@@ -179,7 +180,7 @@ def chain_factor(ks, hess, jac, dx_diag, D):
     N, nb, bmax, qmax, nw = ks.N, ks.nb, ks.bmax, ks.qmax, ks.nw
     neg_d = -np.asarray(D)
     diag_of = lambda u: np.where(u < nw, dx_diag[np.minimum(u, nw - 1)], neg_d[np.maximum(u - nw, 0)])
-    val = lambda src: _gather(ks, src, hess, jac, dx_diag, neg_d)
+    val = lambda src: _gather(ks, src, hess, jac, dx_diag, neg_d, aux)
     F = dict(Sinv=[None] * N, YL=[None] * N, P=[None] * N, Q=[None] * N)
     neg = 0
     carry = None
@@ -258,4 +259,63 @@ def chain_solve(ks, F, rhs):
             x -= F['YL'][n] @ x_next[ks.cr[ks.cr_ptr[n]:ks.cr_ptr[n + 1]]]
         sol[ks.unk[ks.blk_ptr[n]:ks.blk_ptr[n + 1]]] = x
         x_next = x
+    return sol
+
+
+def condensed_factor(cs, hess, jac, dx_diag, D):
+    '''
+    numpy twin of csrc/kkt_condense.cuh + the chain kernels on the reduced system: interiors A_n inverted independently,
+    T_n = B_n' A_n^-1 B_n gathered into the aux values of the reduced chain (aircraft_trajectory_optimization_b200/
+    kkt_condensed.py).  Returns (factors, negative eigenvalues).
+    '''
+    nw = cs.nw
+    neg_d = -np.asarray(D)
+    diag_of = lambda u: np.where(u < nw, dx_diag[np.minimum(u, nw - 1)], neg_d[np.maximum(u - nw, 0)])
+    val = lambda src: _gather(None, src, hess, jac, dx_diag, neg_d)
+    amax, smax = cs.amax, cs.smax
+    neg = 0
+    Ainv, G = [], []
+    Tbuf = np.zeros(cs.NI * smax * smax)
+    for n in range(cs.NI):
+        u = cs.iunk[cs.iu_ptr[n]:cs.iu_ptr[n + 1]]
+        a = len(u)
+        s = cs.su_ptr[n + 1] - cs.su_ptr[n]
+        M = np.zeros((amax, amax))
+        e0, e1 = cs.iA_ptr[n], cs.iA_ptr[n + 1]
+        M.ravel()[cs.iA_pos[e0:e1]] = val(cs.iA_src[e0:e1])
+        M[np.arange(a), np.arange(a)] += diag_of(u)
+        Bm = np.zeros((amax, smax))
+        e0, e1 = cs.iB_ptr[n], cs.iB_ptr[n + 1]
+        Bm.ravel()[cs.iB_pos[e0:e1]] = val(cs.iB_src[e0:e1])
+        Bm = Bm[:a, :s]
+        Ai, ng_ = sym_invert_bp(M[:a, :a])
+        neg += ng_
+        Gn = Ai @ Bm
+        T = np.zeros((smax, smax))
+        T[:s, :s] = Bm.T @ Gn
+        Tbuf[n * smax * smax:(n + 1) * smax * smax] = T.ravel()
+        Ainv.append(Ai), G.append(Gn)
+    aux = np.where(cs.aux_orig >= 0, val(np.maximum(cs.aux_orig, 0)), 0.0)
+    aux -= np.add.reduceat(np.concatenate([Tbuf[cs.aux_c_idx], [0.0]]), cs.aux_c_ptr[:-1]) * (np.diff(cs.aux_c_ptr) > 0)
+    F, ng_ = chain_factor(cs.chain, hess, jac, dx_diag, D, aux=aux)
+    F['Ainv'], F['G'] = Ainv, G
+    return F, neg + ng_
+
+
+def condensed_solve(cs, F, rhs):
+    smax = cs.smax
+    tbuf = np.zeros(cs.NI * smax)
+    y = []
+    for n in range(cs.NI):
+        u = cs.iunk[cs.iu_ptr[n]:cs.iu_ptr[n + 1]]
+        s = cs.su_ptr[n + 1] - cs.su_ptr[n]
+        y.append(F['Ainv'][n] @ rhs[u])
+        tbuf[n * smax:n * smax + s] = F['G'][n].T @ rhs[u]
+    rhs2 = rhs.copy()
+    rhs2[cs.rsep] -= np.add.reduceat(np.concatenate([tbuf[cs.r_c_idx], [0.0]]), cs.r_c_ptr[:-1])
+    sol = chain_solve(cs.chain, F, rhs2)
+    for n in range(cs.NI):
+        u = cs.iunk[cs.iu_ptr[n]:cs.iu_ptr[n + 1]]
+        su = cs.sunk[cs.su_ptr[n]:cs.su_ptr[n + 1]]
+        sol[u] = y[n] - F['G'][n] @ sol[su]
     return sol

@@ -11,8 +11,10 @@ name = sys.argv[1] if len(sys.argv) > 1 else 'race_param_rk4_drone'
 Bs = [int(b) for b in sys.argv[2].split(',')] if len(sys.argv) > 2 else [1, 64, 256, 512]
 prod = build_product(name)
 st, F = prod.structure, prod.functions
-K = KktSolver(st)
+K = KktSolver(st, condensed=False) if os.environ.get('RB_KKT_BIG') else KktSolver(st)
 ks = K.ks
+if K.cs is not None:
+    print('condensed: NI', K.cs.NI, 'amax', K.cs.amax, 'smax', K.cs.smax)
 print(name, 'N', ks.N, 'bmax', ks.bmax, 'nb', ks.nb, 'mmax', ks.mmax, 'qmax', ks.qmax)
 dev = torch.device('cuda', 0)
 x, lam = eval_point(st, 0)

@@ -95,5 +95,10 @@ def test_maximum_size_structures(built_library):
 @pytest.mark.gpu
 def test_kkt_accepts_collocation_structures(built_library):
     from aircraft_trajectory_optimization_b200.kkt import KktSolver
-    K = KktSolver(build_product('fig8_global_colloc_drone', small=True).structure)
-    assert K.ks.bmax > 300 and K.ks.nb < 64
+    st = build_product('fig8_global_colloc_drone', small=True).structure
+    # default: interiors condensed, the reduced system goes through the shared-memory chain kernels
+    K = KktSolver(st)
+    assert K.cs is not None and K.cs.amax > 250 and K.ks.bmax <= 64 and K.ks.nb < 64
+    # the uncondensed chain of large triples (csrc/kkt_big.cuh) stays available
+    K = KktSolver(st, condensed=False)
+    assert K.cs is None and K.ks.bmax > 300 and K.ks.nb < 64

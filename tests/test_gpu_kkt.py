@@ -9,8 +9,10 @@ import pytest
 from cases import CASES, build_case, build_product, eval_point
 
 RK4_CASES = [c for c, v in CASES.items() if v[3]]
-# collocation structures go through the large-block kernel (csrc/kkt_big.cuh)
-KKT_CASES = RK4_CASES + ['fig8_global_colloc_point', 'fig8_global_colloc_drone', 'obs_param_colloc_point']
+# collocation structures: interiors condensed (csrc/kkt_condense.cuh) + chain kernels on the reduced system; the
+# uncondensed large-block kernel (csrc/kkt_big.cuh) is kept and tested on one structure ('@big')
+KKT_CASES = RK4_CASES + ['fig8_global_colloc_point', 'fig8_global_colloc_drone', 'fig8_param_colloc_drone',
+                         'fig8_param_colloc_drone_euler', 'obs_param_colloc_point', 'fig8_global_colloc_point@big']
 
 
 def _inputs(st, F, B, seed=0):
@@ -30,13 +32,14 @@ def test_kkt_solve_matches_sparse_lu(name, built_library):
     import torch
     from oracle.kkt_blocks_ref import sparse_solve, kkt_matrix
     from aircraft_trajectory_optimization_b200.kkt import KktSolver
+    name, _, variant = name.partition('@')
     prod = build_product(name, small=True)
     st, F = prod.structure, prod.functions
     B = 3
     hess, jac, dxd, D, rhs = _inputs(st, F, B)
     dev = torch.device('cuda', 0)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-    K = KktSolver(st)
+    K = KktSolver(st, condensed=False) if variant == 'big' else KktSolver(st)
     th, tj, tdx, tnd, tr = t(hess), t(jac), t(dxd), t(-D), t(rhs)
     sol, status = K.factor_solve(th, tj, tdx, tnd, tr)
     assert int(status[:, 0].abs().sum()) == 0
@@ -66,11 +69,12 @@ def test_kkt_solve_matches_sparse_lu(name, built_library):
 
 
 @pytest.mark.gpu
-def test_kkt_full_size_residual(built_library):
-    ''' full-size C2 structure (N = 490): residual of the refined solution, no CPU solve needed '''
+@pytest.mark.parametrize('name', ['race_param_rk4_drone', 'fig8_global_colloc_drone', 'obs_param_colloc_drone'])
+def test_kkt_full_size_residual(name, built_library):
+    ''' full-size C2 (N = 490), C1 (N = 56), C3 (N = 100) structures: residual of the refined solution '''
     import torch
     from aircraft_trajectory_optimization_b200.kkt import KktSolver
-    prod = build_product('race_param_rk4_drone')
+    prod = build_product(name)
     st, F = prod.structure, prod.functions
     B = 2
     hess, jac, dxd, D, rhs = _inputs(st, F, B, seed=11)
