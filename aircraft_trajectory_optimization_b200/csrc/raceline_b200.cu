@@ -35,6 +35,7 @@
 #include "kkt_condense.cuh"
 #include "mesh_sdf.cuh"
 #include "ipm_glue.cuh"
+#include "warm_start.cuh"
 
 namespace {
 
@@ -656,6 +657,28 @@ int rb_mesh_sdf(const double* tri, int nt, const double* pts, int np, double* di
   mesh_sdf_kernel<<<(unsigned)((np + RB_SDF_THREADS - 1) / RB_SDF_THREADS), RB_SDF_THREADS, 0,
                     static_cast<cudaStream_t>(stream)>>>(tri, nt, pts, np, dist, closest);
   g_launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// batched warm-start chain: point-mass solutions -> drone initial guesses (csrc/warm_start.cuh); device pointers
+static_assert(sizeof(rb_ws_args) == sizeof(RbWsArgs), "rb_ws_args mirrors RbWsArgs");
+int rb_ws_drone_guess(const rb_ws_args* a, void* stream) {
+  if (!a || !a->w_pm || !a->w_dr) return fail("rb_ws_drone_guess: null argument");
+  if (a->B <= 0) return 0;
+  if (!a->global_r && !a->fc) return fail("rb_ws_drone_guess: frame constants are needed when global_r is false");
+  const int nz = a->quat ? 13 : 12;
+  if (a->nw_pm != a->N + a->N * a->P * 12 || a->nw_dr != a->N + a->N * a->P * (nz + 8))
+    return fail("rb_ws_drone_guess: decision vector lengths do not match N, K and the orientation parameters");
+  RbWsArgs r;
+  std::memcpy(&r, a, sizeof(RbWsArgs));
+  r.use_fc = a->fc != nullptr;
+  const long long t = (long long)a->B * a->N * a->P;
+  ws_point_kernel<<<(unsigned)((t + RB_WS_THREADS - 1) / RB_WS_THREADS), RB_WS_THREADS, 0,
+                    static_cast<cudaStream_t>(stream)>>>(r);
+  CK(cudaGetLastError());
+  ws_continuity_kernel<<<(a->B + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(r);
+  g_launches += 2;
   CK(cudaGetLastError());
   return 0;
 }

@@ -698,6 +698,66 @@ class DroneRaceline(BaseRaceline):
             return [float(np.linalg.norm(self.ws_model.f_T(z_ws, u_ws)) / 4)] * 4
         return super()._guess_u(n, k)
 
+    # ---- batched warm-start chain on the device --------------------------------
+    def guess_batch(self, w_pm):
+        '''
+        drone initial guesses of B point-mass solutions (rows of w_pm, decision-vector layout of the warm-start
+        solver) -- the batched form of _guess_z / _guess_u (drone_raceline.py:158-277), csrc/warm_start.cuh.
+        Returns (w0 (B, nw) CUDA tensor clipped to the variable bounds like the NLP start point, info (B, 4)).
+        '''
+        import torch
+        from .warm_start import drone_guess_batch
+        cfg = self.config
+        fc = None
+        if self.parametric and not self.model.config.global_r:
+            s_all = np.array([self._get_s(n, k) for n in range(cfg.N) for k in range(cfg.K + 1)])
+            fc = self.line.frame_constants(s_all)
+        w0, info = drone_guess_batch(w_pm, cfg.N, cfg.K, quat=self.model.config.use_quat, closed=cfg.closed,
+                                     global_r=self.model.config.global_r, fc=fc)
+        return w0, info
+
+    def solve_batch(self, vp_drone, vp_point=None):
+        '''
+        the scripts' chain (point-mass solve -> drone guess -> drone solve, drone_raceline.py:294-312) for B vehicle
+        variants at once, every instance warm-started from its OWN point-mass solution.  vp_drone: (B, 13) vehicle
+        parameters (models.VP_DRONE order); vp_point: (B, 6) (models.VP_POINT), default: the warm-start solver's
+        parameters with the mass of every drone variant.  Instances whose warm start closes the lap with the other
+        quaternion sign / yaw wrap than the one the closure rows were built for (info[:, 0] / info[:, 1]) are reported
+        in `closure_mismatch`; they need a structure of their own.
+        '''
+        from .models import vehicle_params, VP_POINT, VP_DRONE
+        if self.ws_solver is None:
+            raise RuntimeError('solve_batch needs the warm-start solver (generate_ws=True)')
+        vp_drone = np.atleast_2d(np.asarray(vp_drone, dtype=float))
+        B = vp_drone.shape[0]
+        ws = self.ws_solver
+        if vp_point is None:
+            vp_point = np.tile(vehicle_params(ws.vehicle_config), (B, 1))
+            vp_point[:, VP_POINT.index('m')] = vp_drone[:, VP_DRONE.index('m')]
+        wst = ws.structure
+        sol_pm = ws.solver(x0=np.tile(wst.w0, (B, 1)), lbx=wst.lbw, ubx=wst.ubw, lbg=wst.lbg, ubg=wst.ubg, p=vp_point)
+        pm_ok = np.asarray(ws.solver.stats()['success_each'])
+        w0, info = self.guess_batch(sol_pm['x'])
+        info = info.cpu().numpy()
+        st = self.structure
+        X0 = np.clip(w0.cpu().numpy(), st.lbw, st.ubw)
+        sol = self.solver(x0=X0, lbx=st.lbw, ubx=st.ubw, lbg=st.lbg, ubg=st.ubg, p=vp_drone)
+        quat = self.model.config.use_quat
+        ws_known = self._first_ws_r is not None and self._last_ws_r is not None
+        if quat:
+            built_flip = bool(ws_known and np.linalg.norm(self._first_ws_r - self._last_ws_r) > 1)
+            mismatch = info[:, 0].astype(bool) != built_flip
+        else:
+            built_wraps = int(np.round((self._last_ws_r - self._first_ws_r)[0] / 2 / np.pi)) if ws_known else 0
+            mismatch = info[:, 1] != built_wraps
+        sol['lap_time'] = sol['x'][:, :self.config.N].sum(1)
+        sol['lap_time_ws'] = sol_pm['x'][:, :ws.config.N].sum(1)
+        sol['ws_success'] = pm_ok
+        sol['success'] = np.asarray(self.solver.stats()['success_each'])
+        sol['closure_mismatch'] = mismatch | (info[:, 2] > 0)
+        sol['x0'] = X0
+        return sol
+
 
 class GlobalPointRaceline(PointRaceline, BaseGlobalRaceline):
     label, color = 'Global PM', [1, 1, 1, 1]

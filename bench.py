@@ -415,11 +415,97 @@ def run_colloc_eval(dev, local_rank, steps, B=512):
     ms = e0.elapsed_time(e1) / steps
     ab = algorithmic_bytes(st)
     peak, _ = _peaks()
-    return dict(workload='C1: scripts/fig_8.py, global-frame quaternion drone, Legendre collocation N=56 K=7',
+    # KKT factor + solve of C1 (condensed interiors + chain kernels), one instance and one wave, CUDA events
+    kkt = None
+    try:
+        from aircraft_trajectory_optimization_b200.kkt import KktSolver
+        K = KktSolver(st)
+        kkt = dict(path='kktc_interior_factor_kernel (one CTA per interval and instance) + kktc_gather_kernel + '
+                        'kkt_factor_kernel + kkt_solve_kernel on the reduced system + kktc_interior_back_kernel',
+                   interiors=int(K.cs.NI), interior_unknowns=int(K.cs.amax), separator_unknowns=int(K.cs.smax),
+                   reduced_block=int(K.ks.bmax), border=int(K.ks.nb))
+        for Bk in (1, 8):
+            dxd = torch.full((Bk, st.nw), 1e-2, **f64)
+            negd = torch.where(torch.as_tensor(st.lbg == st.ubg, device=dev)[None, :], torch.zeros(Bk, st.ng, **f64),
+                               torch.full((Bk, st.ng), -1.0, **f64))
+            rhs = torch.ones(Bk, st.nw + st.ng, **f64)
+            hj = (outs[4][:Bk].contiguous(), outs[3][:Bk].contiguous())
+            K.factor_solve(*hj, dxd, negd, rhs)
+            torch.cuda.synchronize(dev)
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record()
+            for _ in range(5):
+                K.factor_solve(*hj, dxd, negd, rhs)
+            k1.record()
+            torch.cuda.synchronize(dev)
+            kkt[f'ms_per_factor_solve_B{Bk}'] = k0.elapsed_time(k1) / 5
+    except Exception as exc:
+        kkt = dict(error=repr(exc))
+    return dict(workload='C1: scripts/fig_8.py, global-frame quaternion drone, Legendre collocation N=56 K=7', kkt=kkt,
                 value=B / (ms * 1e-3), unit=UNIT, instances_per_step=B, ms_per_step=ms, nw=st.nw, ng=st.ng,
                 nnz_jac=st.nnz_jac, nnz_hess=st.nnz_hess, algorithmic_bytes_per_eval=ab,
                 roofline=dict(bound='hbm', achieved=ab * B / (ms * 1e-3) / 1e9, peak=peak, unit='GB/s',
                               frac=ab * B / (ms * 1e-3) / 1e9 / peak, kernel='colloc_cells_kernel<PF_drone_quat_global>'))
+
+
+def run_single_solves(dev):
+    '''
+    the reference scripts as ONE problem each (configs 0-3 of BASELINE.json): warm-started drone solve of
+    scripts/fig_8.py (C1, global frame, collocation N=56), scripts/race.py (C2, parametric RK4 N=490),
+    scripts/obstacles.py (C3, collocation N=100, synthetic tube) and the N=200 narrow-gate stand-in (C4).  Every problem
+    is solved twice; the second solve is reported (the first pays CUDA module loading and allocations).
+    '''
+    import contextlib
+    import torch
+    from cases import make_line, synthetic_tube_arrays
+    from aircraft_trajectory_optimization_b200 import raceline as RL
+    from aircraft_trajectory_optimization_b200.collocation import get_collocation_coefficients
+    from aircraft_trajectory_optimization_b200.pytypes import DroneConfig
+    from aircraft_trajectory_optimization_b200.solve_util import solve_util
+
+    def obstacles():
+        line = make_line('obs')
+        cfg = RL.ParametricRacelineConfig(verbose=False, N=100)
+        cfg.closed = True
+        dc = DroneConfig(global_r=True, use_quat=True, collision_radius=0.4)
+        tau = get_collocation_coefficients(cfg.K)[0]
+        ds = (line.s_max() - line.s_min()) / cfg.N
+        sgrid = np.array([line.s_min() + ds * (n + tau[k]) for n in range(cfg.N) for k in range(cfg.K + 1)])
+        tube = RL.ObstacleFreeTube(*synthetic_tube_arrays(sgrid), dc.collision_radius)
+        return RL.ParametricObstacleDroneRaceline(line, cfg, dc, None, tube, generate_ws=True)
+
+    def cpc():
+        line = make_line('fig8cpc')
+        return solve_util(line, global_frame=False, drone=True, use_quaternion=True, global_r=True, use_ws=True,
+                          solve=False, verbose=False, N=200)[0]
+
+    cases = [
+        ('C1 scripts/fig_8.py: global-frame quaternion drone, collocation N=56 K=7, warm-started',
+         lambda: solve_util(make_line('fig8'), global_frame=True, drone=True, use_quaternion=True, global_r=True,
+                            use_ws=True, solve=False, verbose=False, N=50)[0]),
+        ('C2 scripts/race.py: parametric quaternion drone, RK4 N=490, warm-started', build_c2_with_warm_start),
+        ('C3 scripts/obstacles.py: parametric quaternion drone in a tube, collocation N=100 K=7, warm-started', obstacles),
+        ('C4 stand-in: narrow-gate fig-8, parametric collocation N=200 K=7, warm-started', cpc),
+    ]
+    out = []
+    for label, make in cases:
+        try:
+            with contextlib.redirect_stdout(sys.stderr):
+                solver = make()
+                solver.solve()
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                res = solver.solve()
+                torch.cuda.synchronize(dev)
+                dt = time.perf_counter() - t0
+            st = solver.solver.stats()
+            out.append(dict(problem=label, lap_time=float(res.time), wall_s=dt, solver_s=float(solver.solve_time),
+                            iterations=int(st['iter_count']), return_status=str(st['return_status']),
+                            kkt_factorisations=int(st['n_factor']), t_kkt_s=float(st['t_wall_linear_solver']),
+                            t_eval_s=float(st['t_wall_nlp_hess_l']), nw=int(solver.structure.nw), ng=int(solver.structure.ng)))
+        except Exception as exc:        # a side measurement must not take the bench line down
+            out.append(dict(problem=label, error=repr(exc)))
+    return out
 
 
 def run_reference(args):
@@ -462,6 +548,7 @@ def main():
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-solves', action='store_true', help='skip the converged-solves leg')
     ap.add_argument('--no-colloc', action='store_true', help='skip the C1 (collocation) evaluation leg')
+    ap.add_argument('--no-single', action='store_true', help='skip the single-problem solves of the reference scripts')
     ap.add_argument('--solves-batch', type=int, default=2048, help='multi-start instances per GPU in the solves leg')
     ap.add_argument('--solves-window', type=int, default=888, help='instances iterating at a time (continuous batching)')
     ap.add_argument('--solves-refine', type=int, default=4, help='iterative-refinement steps per KKT solve')
@@ -586,6 +673,9 @@ def main():
             colloc = run_colloc_eval(dev, local_rank, max(3, args.steps // 2))
         except Exception as exc:        # a side measurement must not take the bench line down
             colloc = dict(error=repr(exc))
+    single = None
+    if rank == 0 and not args.no_single:
+        single = run_single_solves(dev)
     solves = None
     if not args.no_solves:
         del x_d, l_d, j_d, h_d, gf_d, g_d
@@ -636,7 +726,7 @@ def main():
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              instances_per_step=Be, api='rb_nlp_eval_all (host buffers, pinned)'),
                     gpu_launches=launches, clocks=clocks, roofline=roofline, cpu_baseline=cpu, solves=solves,
-                    collocation=colloc)
+                    collocation=colloc, single_solves=single)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

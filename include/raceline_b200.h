@@ -229,6 +229,24 @@ int rb_kkt_resolve(const rb_kkt* k, int B, const double* hess, const double* jac
 int rb_kkt_matvec(const rb_kkt* k, int B, const double* hess, const double* jac, const double* dx_diag,
                   const double* neg_d, const double* vec, double* out, void* stream);
 
+/* ---- batched warm-start chain --------------------------------------------------------------------
+ * Replaces the per-point Python loop DroneRaceline._guess_z / _guess_u (drone3d/raceline/drone_raceline.py:158-277): B
+ * point-mass raceline solutions [B][N + N*P*12] (decision-vector layout of base_raceline.py:681-713, state (p, v), input
+ * thrust vector, input rate) become B drone initial guesses [B][N + N*P*(nz+8)] (orientation from thrust and velocity,
+ * body velocity and rate, rotor thrusts |T|/4), with the quaternion sign / yaw wrap made continuous along the lap.
+ * info [B][4] (optional): closure flipped (|q_first - q_last| > 1, drone_raceline.py:82-95), yaw wraps, continuity
+ * failures (the reference raises NotImplementedError), reserved.  All pointers are device pointers. */
+typedef struct rb_ws_args {
+  int B, N, P;
+  int quat, closed, global_r, reserved;
+  int nw_pm, nw_dr;
+  const double* w_pm;
+  const double* fc;       /* [N*P][13] frame constants, needed when global_r == 0 */
+  double* w_dr;
+  int* info;
+} rb_ws_args;
+int rb_ws_drone_guess(const rb_ws_args* args, void* stream);
+
 /* ---- fused vector kernels of the interior-point sweep ("K3" of SURVEY.md s2.1) ---------------------------------------
  * They replace the per-iteration vector work IPOPT does around its linear solves inside `self.solver(x0=...)`
  * (drone3d/raceline/base_raceline.py:160-165): optimality error, condensed KKT right-hand side, fraction-to-the-boundary

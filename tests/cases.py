@@ -129,7 +129,7 @@ def build_product(name, small=False, N=None, vehicle_kw=None):
     return cls(*args)
 
 
-def build_oracle(name, small=False, N=None, vehicle_kw=None):
+def build_oracle(name, small=False, N=None, vehicle_kw=None, ws=None):
     from oracle.ref_centerline import RefSplineCenterline
     from oracle.ref_raceline import RefRaceline, RefTube
     name, vehicle_kw = _resolve(name, vehicle_kw)
@@ -151,7 +151,7 @@ def build_oracle(name, small=False, N=None, vehicle_kw=None):
             s_all = np.array([line.s_min() + ds * (n + tau[k]) for n in range(N) for k in range(8)])
             bp, br = synthetic_tube_arrays(s_all)
             rt = RefTube(bp, br, vc.collision_radius)
-    return RefRaceline(line, cfg, vc, frame, vehicle, tube=rt)
+    return RefRaceline(line, cfg, vc, frame, vehicle, tube=rt, ws=ws)
 
 
 def build_case(name, small=False, N=None, vehicle_kw=None):
