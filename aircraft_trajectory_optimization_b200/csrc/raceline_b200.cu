@@ -36,6 +36,7 @@
 #include "mesh_sdf.cuh"
 #include "ipm_glue.cuh"
 #include "warm_start.cuh"
+#include "post.cuh"
 
 namespace {
 
@@ -657,6 +658,41 @@ int rb_mesh_sdf(const double* tri, int nt, const double* pts, int np, double* di
   mesh_sdf_kernel<<<(unsigned)((np + RB_SDF_THREADS - 1) / RB_SDF_THREADS), RB_SDF_THREADS, 0,
                     static_cast<cudaStream_t>(stream)>>>(tri, nt, pts, np, dist, closest);
   g_launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// frame constants of many path lengths on T tracks (csrc/post.cuh); `tabs` is a DEVICE array of T rb_spline_tab records
+static_assert(sizeof(rb_spline_tab) == sizeof(RbSplineTab), "rb_spline_tab mirrors RbSplineTab");
+int rb_centerline_frames(const rb_spline_tab* tabs, int T, const double* s, int M, int s_stride, double* fc, double* xc,
+                         const double* yn, double* xg, void* stream) {
+  if (!tabs || !s || !fc) return fail("rb_centerline_frames: null argument");
+  if ((yn == nullptr) != (xg == nullptr)) return fail("rb_centerline_frames: yn and xg go together");
+  if (T <= 0 || M <= 0) return 0;
+  const long long t = (long long)T * M;
+  centerline_frames_kernel<<<(unsigned)((t + RB_POST_THREADS - 1) / RB_POST_THREADS), RB_POST_THREADS, 0,
+                             static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const RbSplineTab*>(tabs), T, s, M,
+                                                                  s_stride, fc, xc, yn, xg);
+  g_launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// trajectory interpolants of B solutions at M times each (csrc/post.cuh); tp is a [B][N+1] workspace
+int rb_traj_interp(const double* w, int B, int N, int P, int S, const double* tau, const double* D, const double* tq, int M,
+                   int tq_stride, double* tp, double* out, void* stream) {
+  if (!w || !tq || !tp || !out) return fail("rb_traj_interp: null argument");
+  if (P > 1 && (!tau || !D)) return fail("rb_traj_interp: collocation nodes / end weights missing");
+  if (P < 1 || P > 16) return fail("rb_traj_interp: 1 <= K + 1 <= 16");
+  if (B <= 0 || M <= 0) return 0;
+  const int nw = N + N * P * S;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  traj_times_kernel<<<(B + 63) / 64, 64, 0, st>>>(w, B, N, nw, tp);
+  CK(cudaGetLastError());
+  const long long t = (long long)B * M;
+  traj_interp_kernel<<<(unsigned)((t + RB_POST_THREADS - 1) / RB_POST_THREADS), RB_POST_THREADS, 0, st>>>(
+      w, B, N, P, S, nw, tp, tau, D, tq, M, tq_stride, out);
+  g_launches += 2;
   CK(cudaGetLastError());
   return 0;
 }

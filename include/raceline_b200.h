@@ -229,6 +229,27 @@ int rb_kkt_resolve(const rb_kkt* k, int B, const double* hess, const double* jac
 int rb_kkt_matvec(const rb_kkt* k, int B, const double* hess, const double* jac, const double* dx_diag,
                   const double* neg_d, const double* vec, double* out, void* stream);
 
+/* ---- centerline frame tables and trajectory interpolants ------------------------------
+ * rb_centerline_frames replaces the per-point host evaluation of the 15 `param_terms` and of the Darboux frame
+ * (drone3d/centerlines/spline_centerline.py:232-322, :279-294; spline evaluation of drone3d/utils/interp.py:55-84) for M
+ * path lengths on each of T tracks: fc [T][M][13] = Rp (row-major, columns es|ey|en), ks, ky, kn, |xc'| -- the
+ * per-point constants rb_eval_batch takes as fc_b, so track sweeps build their tables on the device.  Optional: xc
+ * [T][M][3]; yn [T][M][2] -> xg [T][M][3] = xc + ey y + en n (global position of a parametric state,
+ * drone3d/dynamics/drone_models.py:306-328).  s is [T][s_stride >= M], or one row shared by all tracks (s_stride 0).
+ * `tabs` is a DEVICE array of T records whose pointers are device pointers (scipy CubicSpline tables: knots, c[4][n-1][3],
+ * value and slope at the last knot). */
+typedef struct rb_spline_tab {
+  int nkx, nkr;
+  const double *kx, *cx, *ex, *kr, *cr, *er;
+} rb_spline_tab;
+int rb_centerline_frames(const rb_spline_tab* tabs, int T, const double* s, int M, int s_stride, double* fc, double* xc,
+                         const double* yn, double* xg, void* stream);
+/* rb_traj_interp replaces the interpolants _unpack_soln builds (drone3d/raceline/base_raceline.py:801-864,
+ * drone3d/utils/discretization_utils.py:53-137): w [B][N + N*P*S] solutions, P = K + 1 points per interval, S values per
+ * point (z, u, du); tq [B][tq_stride >= M] query times (tq_stride 0: shared); tp [B][N+1] workspace; out [B][M][S]. */
+int rb_traj_interp(const double* w, int B, int N, int P, int S, const double* tau, const double* D, const double* tq, int M,
+                   int tq_stride, double* tp, double* out, void* stream);
+
 /* ---- batched warm-start chain --------------------------------------------------------------------
  * Replaces the per-point Python loop DroneRaceline._guess_z / _guess_u (drone3d/raceline/drone_raceline.py:158-277): B
  * point-mass raceline solutions [B][N + N*P*12] (decision-vector layout of base_raceline.py:681-713, state (p, v), input
