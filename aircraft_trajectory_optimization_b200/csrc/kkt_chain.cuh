@@ -80,6 +80,8 @@ struct RbKktChainBatch {
   const double* aux;
   int naux;
   const int* status_add;                        // [B][2] or null
+  // solve kernel only: factor slot of batch row p (re-solves of a subset of the factorised instances); null = p
+  const int* inst;
 };
 
 __device__ __forceinline__ double kf_upd1(double m, double c, double r) { return __fma_rn(-c, r, m); }
@@ -772,11 +774,12 @@ kkt_solve_kernel(const RbKktDev d, const RbKktChainBatch bt) {
   double* racc = xb + nb;                             // [nb] P' z accumulated over the chain
   const double* __restrict__ rhs = bt.rhs + (size_t)p * nk;
   double* __restrict__ sol = bt.sol + (size_t)p * nk;
-  const double* __restrict__ Sinv_g = bt.Sinv + (size_t)p * N * SZ_S;
-  const double* __restrict__ YL_g = bt.YL + (size_t)p * N * SZ_Y;
-  const double* __restrict__ P_g = bt.P + (size_t)p * bt.p_total;
-  const double* __restrict__ Q_g = bt.Q + (size_t)p * bt.q_total;
-  double* __restrict__ Xr = bt.Xr + (size_t)p * N * bmax;
+  const int pf = bt.inst ? bt.inst[p] : p;            // factor slot
+  const double* __restrict__ Sinv_g = bt.Sinv + (size_t)pf * N * SZ_S;
+  const double* __restrict__ YL_g = bt.YL + (size_t)pf * N * SZ_Y;
+  const double* __restrict__ P_g = bt.P + (size_t)pf * bt.p_total;
+  const double* __restrict__ Q_g = bt.Q + (size_t)pf * bt.q_total;
+  double* __restrict__ Xr = bt.Xr + (size_t)pf * N * bmax;
 
   auto bulk = [&](double* dst, const double* src, unsigned doubles, unsigned bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -908,7 +911,7 @@ kkt_solve_kernel(const RbKktDev d, const RbKktChainBatch bt) {
     __syncthreads();
     for (int i = tid; i < nb; i += blockDim.x) {
       double acc = 0.0;
-      for (int j = 0; j < nb; ++j) acc += bt.SB[(size_t)p * nb * nb + i * nb + j] * y[j];
+      for (int j = 0; j < nb; ++j) acc += bt.SB[(size_t)pf * nb * nb + i * nb + j] * y[j];
       xb[i] = acc;
       sol[unkb[i]] = acc;
     }

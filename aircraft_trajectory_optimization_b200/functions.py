@@ -49,7 +49,7 @@ EXPORTS = ['rb_last_error', 'rb_device_count', 'rb_set_device', 'rb_problem_crea
            'rb_problem_nvp', 'rb_sparsity_size', 'rb_sparsity_get', 'rb_eval_scratch_bytes', 'rb_eval_batch',
            'rb_nlp_f', 'rb_nlp_g', 'rb_nlp_grad_f', 'rb_nlp_jac_g', 'rb_nlp_hess_l', 'rb_nlp_eval_all',
            'rb_launch_count', 'rb_profile_enable', 'rb_profile_cell_ms', 'rb_fp64_peak',
-           'rb_kkt_create', 'rb_kkt_set_interiors', 'rb_kkt_destroy', 'rb_kkt_factor_bytes', 'rb_kkt_factor_solve', 'rb_kkt_resolve',
+           'rb_kkt_create', 'rb_kkt_set_interiors', 'rb_kkt_destroy', 'rb_kkt_factor_bytes', 'rb_kkt_factor_solve', 'rb_kkt_resolve', 'rb_kkt_resolve_rows',
            'rb_kkt_matvec', 'rb_casadi_bind', 'rb_mesh_sdf', 'rb_ws_drone_guess', 'rb_centerline_frames', 'rb_traj_interp', 'rb_ipm_error', 'rb_ipm_newton',
            'rb_ipm_direction', 'rb_ipm_trial', 'rb_ipm_trial_merit', 'rb_ipm_update']
 # CasADi generated-code shaped symbols (include/raceline_b200.h, RB_CASADI_DECLARE)

@@ -901,9 +901,16 @@ class CudaBackend:
             # iterative refinement only while some instance is above the fp64 noise floor of its right-hand side;
             # the correction is applied instance by instance, so a result does not depend on the rest of the batch
             need = (r.abs().amax(1) / scale) > self.refine_tol
-            if not bool(need.any()):
+            n_need = int(need.sum())
+            if n_need == 0:
                 break
-            sol = torch.where(need[:, None], sol + self.K.resolve(hess, jac, dx_diag, neg_d, r), sol)
+            if n_need <= rhs.shape[0] // 2 and getattr(self.K, 'can_resolve_rows', False):
+                # the re-solve streams every instance's factors from HBM: run it for the instances that need it only
+                idx = torch.nonzero(need).squeeze(1)
+                dsol = self.K.resolve_rows(idx.to(torch.int32), r.index_select(0, idx).contiguous())
+                sol.index_add_(0, idx, dsol)
+            else:
+                sol = torch.where(need[:, None], sol + self.K.resolve(hess, jac, dx_diag, neg_d, r), sol)
         return sol, status
 
     def kkt_solve(self, hess, jac, dx_diag, neg_d, rhs, refine_steps, idx=None):

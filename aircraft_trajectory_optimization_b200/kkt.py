@@ -409,6 +409,7 @@ def bind_kkt(lib):
     lib.rb_kkt_factor_solve.argtypes = [vp, ctypes.c_int] + [vp] * 9
     lib.rb_kkt_resolve.argtypes = [vp, ctypes.c_int] + [vp] * 8
     lib.rb_kkt_matvec.argtypes = [vp, ctypes.c_int] + [vp] * 7
+    lib.rb_kkt_resolve_rows.argtypes = [vp, ctypes.c_int, ctypes.c_int] + [vp] * 5
 
 
 class KktSolver:
@@ -464,6 +465,7 @@ class KktSolver:
             _check(self.lib.rb_kkt_set_interiors(self.handle, ctypes.byref(di)), 'rb_kkt_set_interiors')
         self._factors = None
         self._factors_B = 0
+        self._last_B = 0
 
     def __del__(self):
         try:
@@ -503,6 +505,7 @@ class KktSolver:
         if status is None:
             status = torch.zeros(B, 2, dtype=torch.int32, device=rhs.device)
         fac = self._factor_buffer(B, rhs.device)
+        self._last_B = B
         if stream is None:
             stream = torch.cuda.current_stream(rhs.device).cuda_stream
         p = self._p
@@ -522,6 +525,25 @@ class KktSolver:
         p = self._p
         self._check(self.lib.rb_kkt_resolve(self.handle, B, p(hess), p(jac), p(dx_diag), p(neg_d), p(rhs), p(sol),
                                             p(self._factors), ctypes.c_void_p(stream)), 'rb_kkt_resolve')
+        return sol
+
+    @property
+    def can_resolve_rows(self):
+        return self.cs is None and self.ks.bmax <= 64 and self.ks.nb <= 64
+
+    def resolve_rows(self, inst, rhs, sol=None, stream=None):
+        ''' solve with the stored factors for a subset: rhs row p belongs to the instance in factor slot inst[p]
+        (int32 CUDA tensor) of the last factor_solve call '''
+        import torch
+        assert inst.dtype == torch.int32 and inst.is_cuda and inst.is_contiguous() and rhs.is_contiguous()
+        assert self._factors is not None and self._last_B >= 1, 'factor_solve first'
+        if sol is None:
+            sol = torch.empty_like(rhs)
+        if stream is None:
+            stream = torch.cuda.current_stream(rhs.device).cuda_stream
+        p = self._p
+        self._check(self.lib.rb_kkt_resolve_rows(self.handle, rhs.shape[0], self._last_B, p(inst), p(rhs), p(sol),
+                                                 p(self._factors), ctypes.c_void_p(stream)), 'rb_kkt_resolve_rows')
         return sol
 
     def matvec(self, hess, jac, dx_diag, neg_d, vec, out=None, stream=None):

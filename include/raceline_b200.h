@@ -225,6 +225,10 @@ int rb_kkt_factor_solve(const rb_kkt* k, int B, const double* hess, const double
 /* solve with the stored factors (the value arrays must be unchanged since rb_kkt_factor_solve) */
 int rb_kkt_resolve(const rb_kkt* k, int B, const double* hess, const double* jac, const double* dx_diag,
                    const double* neg_d, const double* rhs, double* sol, void* factors, void* stream);
+/* the same for a subset of the factorised instances: row p of rhs / sol belongs to factor slot inst[p] (device int array)
+ * of the last rb_kkt_factor_solve call, made with B_factored instances.  Shooting-sized stage blocks only. */
+int rb_kkt_resolve_rows(const rb_kkt* k, int B, int B_factored, const int* inst, const double* rhs, double* sol,
+                        void* factors, void* stream);
 /* out = K vec */
 int rb_kkt_matvec(const rb_kkt* k, int B, const double* hess, const double* jac, const double* dx_diag,
                   const double* neg_d, const double* vec, double* out, void* stream);

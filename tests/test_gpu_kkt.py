@@ -88,3 +88,26 @@ def test_kkt_full_size_residual(name, built_library):
     res = (tr - K.matvec(th, tj, tdx, tnd, sol)).abs().max().item()
     assert int(status[:, 0].abs().sum()) == 0
     assert res <= 1e-8 * max(1.0, float(np.abs(rhs).max()))
+
+
+@pytest.mark.gpu
+def test_resolve_rows_equals_full_resolve(built_library):
+    ''' re-solve for a subset of the factorised instances (rb_kkt_resolve_rows): bit-identical to the rows of the full
+    re-solve, whatever the order of the subset '''
+    import torch
+    from aircraft_trajectory_optimization_b200.kkt import KktSolver
+    prod = build_product('race_param_rk4_drone', small=True)
+    st, F = prod.structure, prod.functions
+    B = 6
+    hess, jac, dxd, D, rhs = _inputs(st, F, B, seed=3)
+    dev = torch.device('cuda', 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    K = KktSolver(st)
+    assert K.can_resolve_rows
+    th, tj, tdx, tnd, tr = t(hess), t(jac), t(dxd), t(-D), t(rhs)
+    K.factor_solve(th, tj, tdx, tnd, tr)
+    r2 = t(np.random.default_rng(5).standard_normal(rhs.shape))
+    full = K.resolve(th, tj, tdx, tnd, r2).cpu().numpy()
+    idx = torch.tensor([4, 1, 5], dtype=torch.int32, device=dev)
+    sub = K.resolve_rows(idx, r2[idx.long()].contiguous()).cpu().numpy()
+    assert np.array_equal(sub, full[[4, 1, 5]])
