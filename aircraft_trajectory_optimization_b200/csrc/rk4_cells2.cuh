@@ -67,8 +67,11 @@ __device__ __forceinline__ void rk4_row_multipliers(const RbDev& d, const double
   }
 }
 
+#ifndef RB_POINT_MINBLOCKS
+#define RB_POINT_MINBLOCKS 1
+#endif
 template <class PF>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, RB_POINT_MINBLOCKS)
 rk4_point_kernel(const RbDev d, const RbBatch b, double* __restrict__ scr) {
   using SC = Rk4Scratch<PF>;
   constexpr int NZ = PF::NZ, NU = PF::NU, NX = PF::NX, NR = NZ + NU, CPB = SC::CPB;
