@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -28,6 +29,7 @@
 #include "generated/pf_drone_quat_param_gr_drag.cuh"
 #include "rk4_cells2.cuh"
 #include "colloc_cells.cuh"
+#include "colloc_gather.cuh"
 #include "simple_rows.cuh"
 #include "kkt_blocks.cuh"
 #include "kkt_big.cuh"
@@ -70,19 +72,20 @@ struct VariantInfo {
   int nz, nu, nvp;
   int rk4_ns;   // scratch doubles per shooting cell (Rk4Scratch<PF>::NS)
   int rk4_cpb;  // cells per CTA of the direction kernel (scratch group size)
+  int nj, nwh, quat;   // non-zeros of df/dx and of sum_i lam_i d2f_i/dx2 per point; quaternion orientation
 };
 #ifndef RB_RK4_CHUNK
 #define RB_RK4_CHUNK 128
 #endif
 //   // instances per launch pair of the shooting kernels (bounds the scratch: NS * 8 B per cell)
 const VariantInfo kVariants[] = {
-    {"drone_quat_global", PF_drone_quat_global::NZ, PF_drone_quat_global::NU, PF_drone_quat_global::NVP, Rk4Scratch<PF_drone_quat_global>::NS, PF_drone_quat_global::CPB},
-    {"drone_quat_param_gr", PF_drone_quat_param_gr::NZ, PF_drone_quat_param_gr::NU, PF_drone_quat_param_gr::NVP, Rk4Scratch<PF_drone_quat_param_gr>::NS, PF_drone_quat_param_gr::CPB},
-    {"point_pm_global", PF_point_pm_global::NZ, PF_point_pm_global::NU, PF_point_pm_global::NVP, Rk4Scratch<PF_point_pm_global>::NS, PF_point_pm_global::CPB},
-    {"point_pm_param_gr", PF_point_pm_param_gr::NZ, PF_point_pm_param_gr::NU, PF_point_pm_param_gr::NVP, Rk4Scratch<PF_point_pm_param_gr>::NS, PF_point_pm_param_gr::CPB},
-    {"drone_ypr_param_gr", PF_drone_ypr_param_gr::NZ, PF_drone_ypr_param_gr::NU, PF_drone_ypr_param_gr::NVP, Rk4Scratch<PF_drone_ypr_param_gr>::NS, PF_drone_ypr_param_gr::CPB},
-    {"drone_ypr_global", PF_drone_ypr_global::NZ, PF_drone_ypr_global::NU, PF_drone_ypr_global::NVP, Rk4Scratch<PF_drone_ypr_global>::NS, PF_drone_ypr_global::CPB},
-#define RB_VARIANT(PF, name) {name, PF::NZ, PF::NU, PF::NVP, Rk4Scratch<PF>::NS, PF::CPB}
+    {"drone_quat_global", PF_drone_quat_global::NZ, PF_drone_quat_global::NU, PF_drone_quat_global::NVP, Rk4Scratch<PF_drone_quat_global>::NS, PF_drone_quat_global::CPB, PF_drone_quat_global::NJ, PF_drone_quat_global::NW, PF_drone_quat_global::QUAT ? 1 : 0},
+    {"drone_quat_param_gr", PF_drone_quat_param_gr::NZ, PF_drone_quat_param_gr::NU, PF_drone_quat_param_gr::NVP, Rk4Scratch<PF_drone_quat_param_gr>::NS, PF_drone_quat_param_gr::CPB, PF_drone_quat_param_gr::NJ, PF_drone_quat_param_gr::NW, PF_drone_quat_param_gr::QUAT ? 1 : 0},
+    {"point_pm_global", PF_point_pm_global::NZ, PF_point_pm_global::NU, PF_point_pm_global::NVP, Rk4Scratch<PF_point_pm_global>::NS, PF_point_pm_global::CPB, PF_point_pm_global::NJ, PF_point_pm_global::NW, PF_point_pm_global::QUAT ? 1 : 0},
+    {"point_pm_param_gr", PF_point_pm_param_gr::NZ, PF_point_pm_param_gr::NU, PF_point_pm_param_gr::NVP, Rk4Scratch<PF_point_pm_param_gr>::NS, PF_point_pm_param_gr::CPB, PF_point_pm_param_gr::NJ, PF_point_pm_param_gr::NW, PF_point_pm_param_gr::QUAT ? 1 : 0},
+    {"drone_ypr_param_gr", PF_drone_ypr_param_gr::NZ, PF_drone_ypr_param_gr::NU, PF_drone_ypr_param_gr::NVP, Rk4Scratch<PF_drone_ypr_param_gr>::NS, PF_drone_ypr_param_gr::CPB, PF_drone_ypr_param_gr::NJ, PF_drone_ypr_param_gr::NW, PF_drone_ypr_param_gr::QUAT ? 1 : 0},
+    {"drone_ypr_global", PF_drone_ypr_global::NZ, PF_drone_ypr_global::NU, PF_drone_ypr_global::NVP, Rk4Scratch<PF_drone_ypr_global>::NS, PF_drone_ypr_global::CPB, PF_drone_ypr_global::NJ, PF_drone_ypr_global::NW, PF_drone_ypr_global::QUAT ? 1 : 0},
+#define RB_VARIANT(PF, name) {name, PF::NZ, PF::NU, PF::NVP, Rk4Scratch<PF>::NS, PF::CPB, PF::NJ, PF::NW, PF::QUAT ? 1 : 0}
     RB_VARIANT(PF_drone_quat_param_lr, "drone_quat_param_lr"),
     RB_VARIANT(PF_drone_ypr_param_lr, "drone_ypr_param_lr"),
     RB_VARIANT(PF_point_pm_param_lr, "point_pm_param_lr"),
@@ -145,9 +148,19 @@ cudaError_t ensure_dyn_smem(const void* func, size_t bytes) {
 }
 template <class PF> struct DirTag {};
 template <class PF> struct CollocTag {};
+struct GatherTag {};
+
+// RB_COLLOC_IMAGE=1 in the environment selects the round-1 shared-memory-image kernel (colloc_cells.cuh) for A/B runs
+bool colloc_image_path() {
+  static const bool on = [] {
+    const char* e = std::getenv("RB_COLLOC_IMAGE");
+    return e && e[0] == '1';
+  }();
+  return on;
+}
 
 template <class PF>
-cudaError_t launch_cells_t(const RbDev& d, const RbBatch& b, cudaStream_t st) {
+cudaError_t launch_cells_t(const RbDev& d, const RbBatch& b, const CgTables* cg, cudaStream_t st) {
   const long long cells = (long long)b.B * d.N;
   if (d.transcription == RB_RK4) {
     constexpr int CPB = RB_CELL_THREADS / (PF::NX + 1);
@@ -199,6 +212,33 @@ cudaError_t launch_cells_t(const RbDev& d, const RbBatch& b, cudaStream_t st) {
       }
     }
     return cudaGetLastError();
+  } else if (cg && b.cell_scr && !colloc_image_path()) {
+    // output-driven form (colloc_gather.cuh): point functions of a chunk of instances, then CTA (n, g) per interval
+    const size_t smem = cg_smem_bytes(PF::NZ, PF::NU, PF::NJ, PF::NW, cg->lstride[0], cg->lstride[1], cg->lptr[0][CG_NKIND],
+                                      cg->lptr[1][CG_NKIND]);
+    cudaError_t e0 = ensure_dyn_smem<GatherTag>((const void*)colloc_gather_kernel, smem);
+    if (e0 != cudaSuccess) return e0;
+    for (int p0 = 0; p0 < b.B; p0 += RB_CG_CHUNK) {
+      RbBatch c = b;
+      c.B = b.B - p0 < RB_CG_CHUNK ? b.B - p0 : RB_CG_CHUNK;
+      c.x += (size_t)p0 * d.nw;
+      if (c.lam_g) c.lam_g += (size_t)p0 * d.ng;
+      if (c.lam_f) c.lam_f += p0;
+      c.vp += (size_t)p0 * b.vp_stride;
+      if (c.fc_b) c.fc_b += (size_t)p0 * d.N * (d.K + 1) * PF::NFC;
+      if (c.grad_f) c.grad_f += (size_t)p0 * d.nw;
+      if (c.g) c.g += (size_t)p0 * d.ng;
+      if (c.jac) c.jac += (size_t)p0 * d.nnzj;
+      if (c.hess) c.hess += (size_t)p0 * d.nnzh;
+      if (c.fpart) c.fpart += (size_t)p0 * d.N;
+      const long long cc = (long long)c.B * d.N;
+      colloc_point_kernel<PF><<<(unsigned)((cc * 7 + 127) / 128), 128, 0, st>>>(d, c, b.cell_scr);
+      // one CTA per cell: ~10 CTAs per SM overlap each other's staging latency
+      const int G = c.B;
+      colloc_gather_kernel<<<dim3((unsigned)d.N, (unsigned)G), RB_CG_THREADS, smem, st>>>(d, c, *cg, b.cell_scr);
+      g_launches += 2;
+    }
+    return cudaGetLastError();
   } else {
     const long long blocks = (cells + RB_COLLOC_WPB - 1) / RB_COLLOC_WPB;
     const size_t smem = sizeof(double) * RB_COLLOC_WPB * (size_t)colloc_cell_doubles<PF>(d.cell_nj, d.cell_nh);
@@ -210,19 +250,19 @@ cudaError_t launch_cells_t(const RbDev& d, const RbBatch& b, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_cells(int variant, const RbDev& d, const RbBatch& b, cudaStream_t st) {
+cudaError_t launch_cells(int variant, const RbDev& d, const RbBatch& b, const CgTables* cg, cudaStream_t st) {
   switch (variant) {
-    case 0: return launch_cells_t<PF_drone_quat_global>(d, b, st);
-    case 1: return launch_cells_t<PF_drone_quat_param_gr>(d, b, st);
-    case 2: return launch_cells_t<PF_point_pm_global>(d, b, st);
-    case 3: return launch_cells_t<PF_point_pm_param_gr>(d, b, st);
-    case 4: return launch_cells_t<PF_drone_ypr_param_gr>(d, b, st);
-    case 5: return launch_cells_t<PF_drone_ypr_global>(d, b, st);
-    case 6: return launch_cells_t<PF_drone_quat_param_lr>(d, b, st);
-    case 7: return launch_cells_t<PF_drone_ypr_param_lr>(d, b, st);
-    case 8: return launch_cells_t<PF_point_pm_param_lr>(d, b, st);
-    case 9: return launch_cells_t<PF_drone_quat_global_drag>(d, b, st);
-    case 10: return launch_cells_t<PF_drone_quat_param_gr_drag>(d, b, st);
+    case 0: return launch_cells_t<PF_drone_quat_global>(d, b, cg, st);
+    case 1: return launch_cells_t<PF_drone_quat_param_gr>(d, b, cg, st);
+    case 2: return launch_cells_t<PF_point_pm_global>(d, b, cg, st);
+    case 3: return launch_cells_t<PF_point_pm_param_gr>(d, b, cg, st);
+    case 4: return launch_cells_t<PF_drone_ypr_param_gr>(d, b, cg, st);
+    case 5: return launch_cells_t<PF_drone_ypr_global>(d, b, cg, st);
+    case 6: return launch_cells_t<PF_drone_quat_param_lr>(d, b, cg, st);
+    case 7: return launch_cells_t<PF_drone_ypr_param_lr>(d, b, cg, st);
+    case 8: return launch_cells_t<PF_point_pm_param_lr>(d, b, cg, st);
+    case 9: return launch_cells_t<PF_drone_quat_global_drag>(d, b, cg, st);
+    case 10: return launch_cells_t<PF_drone_quat_param_gr_drag>(d, b, cg, st);
   }
   return cudaErrorInvalidValue;
 }
@@ -247,6 +287,8 @@ struct rb_problem {
   std::vector<long long> jac_sp, hess_sp;
   Workspace ws;
   std::mutex mu;
+  CgTables cg{};            // collocation: per-entry recipes of the output-driven kernel (colloc_gather.cuh)
+  bool has_cg = false;
 };
 
 namespace {
@@ -298,6 +340,127 @@ int ensure_ws(rb_problem* p, int B) {
 }
 
 }  // namespace
+
+
+// per-entry recipes of colloc_gather_kernel from the slot -> unique-entry template (structure_colloc.py: CollocLayout,
+// _template): every local contribution slot has a fixed formula; the contributions of a unique entry are listed together
+static int build_gather_tables(rb_problem* p, const rb_problem_desc* s) {
+  const VariantInfo& vi = kVariants[p->variant];
+  const int nz = p->nz, nu = p->nu, nx = nz + nu, S = nz + 2 * nu, NJ = vi.nj, NW = vi.nwh, KP = 8;
+  const int JS = 0, JF = JS + KP * 9, JC = JF + 7 * NJ, JH = JC + 7 * nz * KP, JD = JH + 7 * nz, JE = JD + KP * nu * 10,
+            JEP = JE + nz * KP * 4, JEU = JEP + nz, JEUP = JEU + nu * KP, NJS = JEUP + nu;
+  const int HW = 0, HUU = HW + 7 * NW, HDD = HUU + KP * nu, HHZ = HDD + KP * nu, HHU = HHZ + KP * nz, HHD = HHU + KP * nu,
+            HHH = HHD + KP * nu, HQ = HHH + 1, NHS = HQ + 32 * 32;
+  if (s->n_tmpl_j != NJS || s->n_tmpl_h != NHS) return fail("collocation template sizes do not match the model variant");
+  const double *C = s->colloc_C, *D = s->colloc_D, *B = s->colloc_B;
+  struct Rec { int ka; double c; };
+  std::vector<Rec> jr(NJS, Rec{-1, 0.0}), hr(NHS, Rec{-1, 0.0});
+  auto ka = [](int kind, int arg) { return (kind << 24) | arg; };
+  for (int k = 0; k < KP; ++k) {
+    for (int j = 0; j < KP; ++j) jr[JS + k * 9 + j] = Rec{ka(CG_HI, 0), C[j * KP + k]};
+    jr[JS + k * 9 + 8] = Rec{ka(CG_PHI2, k), -1.0};
+  }
+  for (int k = 1; k < KP; ++k) {
+    for (int e = 0; e < NJ; ++e) jr[JF + (k - 1) * NJ + e] = Rec{ka(CG_SCR, (nz + e) * 7 + (k - 1)), 0.0};
+    for (int i = 0; i < nz; ++i) {
+      for (int j = 0; j < KP; ++j) jr[JC + ((k - 1) * nz + i) * KP + j] = Rec{ka(CG_HI, 0), -C[j * KP + k]};
+      jr[JH + (k - 1) * nz + i] = Rec{ka(CG_PHI2, 8 + (k - 1) * nz + i), 1.0};
+    }
+  }
+  for (int k = 0; k < KP; ++k)
+    for (int j = 0; j < nu; ++j) {
+      const int t = k * nu + j, b0 = JD + t * 10;
+      for (int m = 0; m < KP; ++m) jr[b0 + m] = Rec{ka(CG_HI, 0), -C[m * KP + k]};
+      jr[b0 + 8] = Rec{ka(CG_CONST, 0), 1.0};
+      jr[b0 + 9] = Rec{ka(CG_PHI2, 8 + 7 * nz + t), 1.0};
+    }
+  for (int c = 0; c < nz; ++c) {
+    const bool isq = vi.quat && c >= 3 && c < 7;
+    for (int k = 0; k < KP; ++k) {
+      if (isq) {
+        for (int bb = 0; bb < 4; ++bb) jr[JE + (c * KP + k) * 4 + bb] = Rec{ka(CG_ENDQ, c | ((c - 3) << 8) | (bb << 12)), D[k]};
+      } else {
+        jr[JE + (c * KP + k) * 4] = Rec{ka(CG_END, c), D[k]};
+      }
+    }
+    jr[JEP + c] = Rec{ka(CG_PARTNER, c), 0.0};
+  }
+  for (int j = 0; j < nu; ++j) {
+    for (int k = 0; k < KP; ++k) jr[JEU + j * KP + k] = Rec{ka(CG_END, nz + j), D[k]};
+    jr[JEUP + j] = Rec{ka(CG_PARTNER, nz + j), 0.0};
+  }
+  for (int k = 1; k < KP; ++k)
+    for (int e = 0; e < NW; ++e) hr[HW + (k - 1) * NW + e] = Rec{ka(CG_SCR, (nz + NJ + e) * 7 + (k - 1)), 0.0};
+  for (int k = 0; k < KP; ++k)
+    for (int j = 0; j < nu; ++j) {
+      const int t = k * nu + j;
+      hr[HUU + t] = Rec{ka(CG_SIGH, 0), 2.0 * s->R[j] * B[k]};
+      hr[HDD + t] = Rec{ka(CG_SIGH, 0), 2.0 * s->dR[j] * B[k]};
+      hr[HHD + t] = Rec{ka(CG_SIGX, 1 + k * S + nx + j), 2.0 * s->dR[j] * B[k]};
+      hr[HHU + t] = Rec{ka(CG_HHU, (1 + k * S + nz + j) | (t << 12)), 2.0 * s->R[j] * B[k]};
+    }
+  for (int j = 0; j < KP; ++j)
+    for (int i = 0; i < nz; ++i) hr[HHZ + j * nz + i] = Rec{ka(CG_QHI2, 8 * nu + j * nz + i), 0.0};
+  hr[HHH] = Rec{ka(CG_HHH, 0), 0.0};
+  for (int pq = 0; pq < 32; ++pq)
+    for (int qq = 0; qq < 32; ++qq)
+      hr[HQ + pq * 32 + qq] = Rec{ka(CG_HQ, (pq & 3) | ((qq & 3) << 4)), D[pq >> 2] * D[qq >> 2]};
+  CgTables& t = p->cg;
+  t.nz = nz;
+  t.nu = nu;
+  t.NJ = NJ;
+  t.NW = NW;
+  t.quat = vi.quat;
+  auto lists = [&](const std::vector<Rec>& rec, const int32_t* tmpl, int nslot, int nuniq, int w, const int32_t* cslot) {
+    std::vector<std::vector<int>> by(nuniq);
+    for (int sidx = 0; sidx < nslot; ++sidx)
+      if (tmpl[sidx] >= 0) {
+        if (tmpl[sidx] >= nuniq || rec[sidx].ka < 0) return 1;
+        by[tmpl[sidx]].push_back(sidx);
+      }
+    std::vector<int32_t> lu, la, mu, mptr(1, 0), mka;
+    std::vector<double> lc, mc;
+    for (int kind = 0; kind < CG_NKIND; ++kind) {
+      t.lptr[w][kind] = (int)lu.size();
+      for (int u = 0; u < nuniq; ++u)
+        if (by[u].size() == 1 && (rec[by[u][0]].ka >> 24) == kind) {
+          lu.push_back(u);
+          la.push_back(rec[by[u][0]].ka);
+          lc.push_back(rec[by[u][0]].c);
+        }
+    }
+    t.lptr[w][CG_NKIND] = (int)lu.size();
+    for (int u = 0; u < nuniq; ++u)
+      if (by[u].size() > 1) {
+        mu.push_back(u);
+        for (int sidx : by[u]) {
+          mka.push_back(rec[sidx].ka);
+          mc.push_back(rec[sidx].c);
+        }
+        mptr.push_back((int32_t)mka.size());
+      }
+    t.nmulti[w] = (int)mu.size();
+    t.lstride[w] = (int)(lu.size() + mu.size());
+    std::vector<int32_t> ls((size_t)s->N * t.lstride[w]);
+    for (int n = 0; n < s->N; ++n) {
+      int32_t* row = ls.data() + (size_t)n * t.lstride[w];
+      for (size_t i = 0; i < lu.size(); ++i) row[i] = cslot[(size_t)n * nuniq + lu[i]];
+      for (size_t i = 0; i < mu.size(); ++i) row[lu.size() + i] = cslot[(size_t)n * nuniq + mu[i]];
+    }
+    int rc = 0;
+    rc |= upload(p, ls.data(), ls.size(), &t.lslot[w]);
+    rc |= upload(p, la.data(), la.size(), &t.la[w]);
+    rc |= upload(p, lc.data(), lc.size(), &t.lc[w]);
+    rc |= upload(p, mptr.data(), mptr.size(), &t.mptr[w]);
+    rc |= upload(p, mka.data(), mka.size(), &t.mka[w]);
+    rc |= upload(p, mc.data(), mc.size(), &t.mc[w]);
+    return rc;
+  };
+  if (lists(jr, s->tmpl_j, NJS, s->cell_nj, 0, s->cell_jslot)) return fail("collocation template: entry without a recipe");
+  if (lists(hr, s->tmpl_h, NHS, s->cell_nh, 1, s->cell_hslot)) return fail("collocation template: entry without a recipe");
+  p->has_cg = true;
+  return 0;
+}
 
 static void cas_forget(rb_problem* p);
 
@@ -373,6 +536,10 @@ int rb_problem_create(const rb_problem_desc* s, rb_problem** out) {
     rc |= upload(p, s->colloc_C, (size_t)P * P, &d.colloc_C);
     rc |= upload(p, s->colloc_D, (size_t)P, &d.colloc_D);
     rc |= upload(p, s->colloc_B, (size_t)P, &d.colloc_B);
+    if (!rc && build_gather_tables(p, s)) {
+      rb_problem_destroy(p);
+      return 1;
+    }
   }
   if (s->n_srow > 0) {
     rc |= upload(p, s->srow_row, (size_t)s->n_srow, &d.srow_row);
@@ -453,6 +620,9 @@ size_t rb_eval_scratch_bytes(const rb_problem* p, int B) {
     const int cpb = kVariants[p->variant].rk4_cpb;
     // two halves: consecutive chunks run on two streams
     n += 2 * (size_t)((cells + cpb - 1) / cpb) * kVariants[p->variant].rk4_ns * cpb * sizeof(double);
+  } else if (p->has_cg) {
+    const long long cells = (long long)(B < RB_CG_CHUNK ? B : RB_CG_CHUNK) * p->d.N;
+    n += cg_scratch_doubles(cells, p->nz, kVariants[p->variant].nj, kVariants[p->variant].nwh) * sizeof(double);
   }
   return n;
 }
@@ -496,7 +666,7 @@ int rb_eval_batch(const rb_problem* p, int B, const double* x, const double* lam
     g_timer.used++;
     CK(cudaEventRecord(ev0, st));
   }
-  CK(launch_cells(p->variant, d, b, st));
+  CK(launch_cells(p->variant, d, b, p->has_cg ? &p->cg : nullptr, st));
   if (ev1) CK(cudaEventRecord(ev1, st));
   if (d.n_srow > 0 && (g || jac)) {
     const long long t = (long long)B * d.n_srow;

@@ -445,7 +445,8 @@ def run_colloc_eval(dev, local_rank, steps, B=512):
                 value=B / (ms * 1e-3), unit=UNIT, instances_per_step=B, ms_per_step=ms, nw=st.nw, ng=st.ng,
                 nnz_jac=st.nnz_jac, nnz_hess=st.nnz_hess, algorithmic_bytes_per_eval=ab,
                 roofline=dict(bound='hbm', achieved=ab * B / (ms * 1e-3) / 1e9, peak=peak, unit='GB/s',
-                              frac=ab * B / (ms * 1e-3) / 1e9 / peak, kernel='colloc_cells_kernel<PF_drone_quat_global>'))
+                              frac=ab * B / (ms * 1e-3) / 1e9 / peak,
+                              kernel='colloc_point_kernel<PF_drone_quat_global> + colloc_gather_kernel (all chunks of a step)'))
 
 
 def run_single_solves(dev):
