@@ -699,10 +699,10 @@ def main():
         nj, nwz = len(meta['J']), len(meta['W'])
         flop_eval = st.N * (4 * (meta['ops']['fJ_s'] + meta['ops']['vjpW_s']) + nv * 4 * (2 * nj + 2 * nwz))
         # DRAM bytes of the two shooting kernels per 128-instance chunk, from the ncu --set full capture of this
-        # command (profiles/r01_ncu_rk4_cells.txt: point 32.3 + 443.6 MB, direction 453.0 + 176.8 MB), scaled to a step
-        traffic_bytes = (32.323328e6 + 443.590144e6 + 453.005056e6 + 176.750336e6) * (B / 128.0)
+        # command (profiles/r02_ncu_rk4.txt: point 31.7 + 442.6 MB, direction 453.1 + 177.1 MB), scaled to a step
+        traffic_bytes = (31.672576e6 + 442.574848e6 + 453.142016e6 + 177.075968e6) * (B / 128.0)
         roofline = dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
-                        traffic=traffic_bytes, traffic_unit='bytes per step (ncu dram__bytes_read+write, profiles/r01_ncu_rk4_cells.txt)',
+                        traffic=traffic_bytes, traffic_unit='bytes per step (ncu dram__bytes_read+write of one --set full capture of this command, profiles/r02_ncu_rk4.txt; not re-measured in this run)',
                         algorithmic_bytes_per_step=ab * B, peak_source=peak_src, kernel='rk4_point_kernel + rk4_dir_kernel <PF_drone_quat_param_gr> (all chunks of a step)',
                         algorithmic_bytes_per_eval=ab, evals_per_launch=B, kernel_ms=cell_avg_ms,
                         kernel_share_of_step=cell_ms.value / total_ms,

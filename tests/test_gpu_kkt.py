@@ -56,9 +56,9 @@ def test_kkt_solve_matches_sparse_lu(name, built_library):
         scale = np.abs(ref).max()
         # K v product: bit-for-bit the same sum up to ordering
         assert np.abs(Km @ sol[b] - kv[b]).max() <= 1e-9 * max(1.0, np.abs(kv[b]).max())
-        # (the unrefined block solve is only as good as the conditioning of the explicit block inverses allows;
-        # the driver always refines)
-        assert np.abs(sol[b] - ref).max() <= 0.5 * scale, (np.abs(sol[b] - ref).max(), scale)
+        # the unrefined block solve (explicit block inverses): measured 1e-14 .. 3.4e-9 relative on these matrices
+        # (tests/gpu_kkt_accuracy.py); the interior-point matrices are worse conditioned, hence the driver's refinement
+        assert np.abs(sol[b] - ref).max() <= 1e-6 * scale, (np.abs(sol[b] - ref).max(), scale)
         # refined: residual at fp64 level, solution equal to SuperLU's within conditioning
         assert np.abs(Km @ sol2[b] - rhs[b]).max() <= 1e-9 * max(1.0, np.abs(rhs[b]).max())
         assert np.abs(sol2[b] - ref).max() <= 1e-7 * scale, (np.abs(sol2[b] - ref).max(), scale)
