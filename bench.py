@@ -509,6 +509,46 @@ def run_single_solves(dev):
     return out
 
 
+def run_measured_cpu_solve(dev):
+    '''
+    a MEASURED converged-solve comparison at full size with the same interior-point driver on both sides: the warm-start
+    NLP of scripts/race.py (parametric point mass, RK4 N=490, 6370 variables, cold start).  CPU: oracle tapes (interpreted
+    SX evaluation, the reference's execution model) + SuperLU on one core (oracle/cpu_backend.py); GPU: the product path.
+    The drone NLP of C2 is not run on the CPU: its full-size tape takes minutes to build.
+    '''
+    import contextlib
+    import torch
+    from cases import build_oracle, build_product
+    from oracle.nlp_functions import OracleNLP
+    from oracle.cpu_backend import OracleBackend
+    from aircraft_trajectory_optimization_b200.ipm import InteriorPoint, IpmOptions
+    name = 'race_param_rk4_point'
+    out = dict(problem='warm-start NLP of scripts/race.py: parametric point mass, RK4 N=490 (cold start)')
+    with contextlib.redirect_stdout(sys.stderr):
+        prod = build_product(name)
+        prod.solve()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        res = prod.solve()
+        torch.cuda.synchronize(dev)
+        out['gpu'] = dict(wall_s=time.perf_counter() - t0, lap_time=float(res.time), iterations=int(prod.solver.stats()['iter_count']),
+                          return_status=str(prod.solver.stats()['return_status']))
+        t0 = time.perf_counter()
+        ref = build_oracle(name)
+        nlp = OracleNLP(ref)
+        t_build = time.perf_counter() - t0
+        T = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64))
+        ip = InteriorPoint(OracleBackend(nlp, nlp), IpmOptions(max_iter=1000, verbose=False))
+        t0 = time.perf_counter()
+        r = ip.solve(T(ref.w0[None]), T(ref.lbw), T(ref.ubw), T(ref.lbg), T(ref.ubg))
+        dt = time.perf_counter() - t0
+    out['cpu'] = dict(wall_s=dt, lap_time=float(r.x[0, :ref.config.N].sum()), iterations=int(r.iterations[0]), cores=1,
+                      t_eval_s=float(r.t_eval), t_kkt_s=float(r.t_kkt), tape_build_s=t_build,
+                      kind='port: oracle tape interpreter + scipy SuperLU, same interior-point driver')
+    out['speedup_single_instance'] = dt / out['gpu']['wall_s']
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -677,6 +717,11 @@ def main():
     single = None
     if rank == 0 and not args.no_single:
         single = run_single_solves(dev)
+        if not args.no_cpu:
+            try:
+                single.append(run_measured_cpu_solve(dev))
+            except Exception as exc:        # a side measurement must not take the bench line down
+                single.append(dict(problem='measured CPU solve', error=repr(exc)))
     solves = None
     if not args.no_solves:
         del x_d, l_d, j_d, h_d, gf_d, g_d
