@@ -69,7 +69,7 @@ class InteriorPointSolver:
                            return_status=RETURN_STATUS[int(st.max())] if single else [RETURN_STATUS[int(k)] for k in st],
                            success_each=r.success.cpu().numpy(), iterations_each=r.iterations.cpu().numpy(),
                            t_wall_nlp_hess_l=r.t_eval, t_wall_linear_solver=r.t_kkt, t_wall_total=r.t_total,
-                           n_eval=r.n_eval, n_factor=r.n_factor)
+                           n_eval=r.n_eval, n_factor=r.n_factor, n_soc=getattr(r, 'n_soc', 0))
         out = {'x': r.x.cpu().numpy(), 'f': r.f.cpu().numpy(), 'g': r.g.cpu().numpy(),
                'lam_x': r.lam_x.cpu().numpy(), 'lam_g': r.lam_g.cpu().numpy(), 'lam_p': np.zeros(0)}
         if single:

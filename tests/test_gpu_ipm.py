@@ -168,3 +168,36 @@ def test_fused_sweep_kernels_first_iterations_on_drone_problems(name, built_libr
     for k in ('x', 'lam_g', 'lam_x', 'g'):
         scale = max(1.0, np.abs(sols[False][k]).max())
         assert np.abs(sols[True][k] - sols[False][k]).max() <= 1e-9 * scale, k
+
+
+@pytest.mark.gpu
+def test_second_order_correction_reaches_the_same_minimum(built_library):
+    ''' IPOPT's second-order correction (IpmOptions.max_soc, off by default): corrected steps are taken on a perturbed
+    multi-start batch and the results are KKT points '''
+    from aircraft_trajectory_optimization_b200.ipm import IpmOptions
+    prod = build_product('race_param_rk4_point', N=7)
+    st = prod.structure
+    prod.solver.verbose = False
+    rng = np.random.default_rng(3)
+    X0 = np.clip(np.tile(st.w0, (6, 1)) + 0.02 * rng.standard_normal((6, st.nw)) * np.maximum(np.abs(st.w0), 0.1), st.lbw, st.ubw)
+    X0[0] = st.w0
+    kw = dict(lbx=st.lbw, ubx=st.ubw, lbg=st.lbg, ubg=st.ubg)
+    prod.solver.options = IpmOptions(max_soc=0)
+    base = prod.solver(x0=X0, **kw)
+    ok0 = prod.solver.stats()['success_each']
+    prod.solver.options = IpmOptions(max_soc=4)
+    soc = prod.solver(x0=X0, **kw)
+    ok1 = prod.solver.stats()['success_each']
+    assert prod.solver.stats()['n_soc'] > 0
+    assert ok0.sum() >= 5 and ok1.sum() >= 5
+    lap0, lap1 = base['x'][:, :st.N].sum(1), soc['x'][:, :st.N].sum(1)
+    # this coarse, non-convex problem has several neighbouring local minima (laps 5.80 .. 5.82): the corrected steps
+    # change the path and may end in another one of them (nominal start: 5.8204 without, 5.8108 with the correction), so
+    # the check is that every result is a KKT point of the same NLP, verified independently with the oracle's functions
+    assert np.abs(lap1[ok1] - lap0[0]).max() < 0.05 and np.abs(lap0[ok0] - lap0[0]).max() < 0.05
+    from oracle.nlp_functions import OracleNLP
+    from test_ipm_cpu import _kkt_conditions
+    from cases import build_oracle
+    nlp = OracleNLP(build_oracle('race_param_rk4_point', N=7), build_hess=False)
+    for b in np.nonzero(ok1)[0][:3]:
+        _kkt_conditions(st, nlp, soc['x'][b], soc['lam_g'][b], soc['lam_x'][b])
