@@ -11,9 +11,15 @@
 #pragma once
 #include "kkt_blocks.cuh"
 
-#define RB_KKTB_THREADS 1024
-
-#define RB_KKTB_GRP 8      // Gauss-Jordan update vectors accumulated before one pass over the block applies them
+// threads per CTA and Gauss-Jordan update vectors accumulated before one pass over the block applies them.  Measured on the
+// condensed C1 factorisation (56 interiors of 276 unknowns, ms per factor + solve): 1024 threads / groups of 8: 4.05,
+// 1024 / 16: 4.56, 512 / 8: 3.87, 256 / 16: 3.91, 384 / 24: 3.38, 512 / 16: 3.35 (groups of 32 do not fit shared memory)
+#ifndef RB_KKTB_THREADS
+#define RB_KKTB_THREADS 512
+#endif
+#ifndef RB_KKTB_GRP
+#define RB_KKTB_GRP 16
+#endif
 
 struct KktBigSmem {
   double *Cg, *Rg;          // [RB_KKTB_GRP][nbb] update vectors of the current group
