@@ -35,7 +35,10 @@
 #ifndef RB_KF_EXP
 #define RB_KF_EXP 0
 #endif
-#define RB_KF_THREADS 192   // warp 0: pivot search; warps 1..5: 4 x 4 tiles of the upper triangle (up to 16 x 16 tiles)
+#ifndef RB_KF_THREADS
+#define RB_KF_THREADS 192
+#endif
+// RB_KF_THREADS: warp 0: pivot search; warps 1..5: 4 x 4 tiles of the upper triangle (up to 16 x 16 tiles)
 #define RB_KF_VPAD 72       // update vectors: largest block (64) + tile overhang
 #define RB_KS_THREADS 256
 #define RB_KS_STAGES 3
