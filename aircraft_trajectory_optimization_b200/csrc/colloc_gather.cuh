@@ -38,23 +38,22 @@ enum {
 };
 
 #define CG_NKIND 13
-// Entries with ONE contribution (almost all) are listed per kind -- tight loops, no divergence: list[w] covers
-// lptr[w][k] .. lptr[w][k+1] of (lu = unique entry id, la = argument, lc = constant), w = 0 Jacobian, 1 Hessian.  The few
-// entries with several contributions (e.g. the own-point stencil term next to a df/dx entry) keep a CSR list of
-// (kind << 24 | arg, constant) pairs: entry mu[i], contributions mptr[i] .. mptr[i+1].
+// Entries with ONE contribution (almost all) are listed per kind -- tight loops, no divergence: kind k covers the records
+// lptr[0][k] .. lptr[0][k+1] (Jacobian entries, then Hessian entries; index 1 of the two-element arrays is unused since the
+// two lists were merged).  The few entries with several contributions (e.g. the own-point stencil term next to a df/dx
+// entry) keep a CSR list of (kind << 24 | arg, constant) pairs: contributions mptr[0][i] .. mptr[0][i+1] of multi entry i.
 struct CgTables {
   int nz, nu, NJ, NW, quat;
   int lptr[2][CG_NKIND + 1];
-  const int32_t* la[2];      // kind << 24 | argument
-  const double* lc[2];
   int nmulti[2];
   const int32_t *mptr[2], *mka[2];
   const double* mc[2];
-  // CCS position of every list element per interval: lslot[w][n * lstride[w] + i], first the per-kind lists in order,
-  // then the multi-contribution entries (-1 where the interval lacks the row): one coalesced load instead of the
-  // dependent pair entry id -> per-cell slot table
+  // One 16-byte record per list element and interval: rec[0][n * lstride[0] + i] = (CCS position or -1 where the interval
+  // lacks the row, kind << 24 | Hessian flag << 23 | argument, constant as two words); first the per-kind lists in order,
+  // then the multi-contribution entries (position and flag only).  One LDG.128 per entry instead of three loads plus an
+  // indirection (C1: 658 k -> 733 k evals/s).
   int lstride[2];
-  const int32_t* lslot[2];
+  const int4* rec[2];
 };
 
 #define RB_CG_THREADS 128
@@ -174,49 +173,48 @@ __device__ __forceinline__ double cg_eval(int ka, double c, const double* __rest
   return 0.0;
 }
 
-struct CgLists {      // the interval's recipe lists
-  const int32_t *slot[2], *arg[2];
-  const double* cst[2];
+struct CgLists {      // the interval's recipe records
+  const int4* rec[2];
 };
 
-// all single-contribution entries of one kind: out[CCS position of the entry] = term.  One tight loop per kind (no
-// divergence, no switch); measured faster than a single kind-sorted loop with a switch (636 k against 569 k evals/s on C1).
+// all single-contribution entries of one kind: out[CCS position of the entry] = term, Jacobian and Hessian entries in one
+// list (bit 23 of the argument word selects the output).  One tight loop per kind (no divergence, no switch); measured
+// faster than a single kind-sorted loop with a switch (636 k against 569 k evals/s on C1).
 template <int KIND>
-__device__ __forceinline__ void cg_kind_loop(const CgTables& t, const CgLists& L, int w, double* __restrict__ out,
-                                             const double* __restrict__ cs, const CgOff& o) {
-  const int32_t* __restrict__ sl = L.slot[w];
-  const int32_t* __restrict__ sa = L.arg[w];
-  const double* __restrict__ sc = L.cst[w];
+__device__ __forceinline__ void cg_kind_loop(const CgTables& t, const int4* __restrict__ rec, double* __restrict__ outJ,
+                                             double* __restrict__ outH, const double* __restrict__ cs, const CgOff& o) {
 #pragma unroll 2
-  for (int i = t.lptr[w][KIND] + threadIdx.x; i < t.lptr[w][KIND + 1]; i += RB_CG_THREADS) {
-    const int slot = sl[i];
-    if (slot >= 0) out[slot] = cg_term<KIND>(sa[i] & 0xffffff, sc[i], cs, o);
+  for (int i = t.lptr[0][KIND] + threadIdx.x; i < t.lptr[0][KIND + 1]; i += RB_CG_THREADS) {
+    const int4 r = __ldg(rec + i);
+    double* __restrict__ out = (r.y & 0x800000) ? outH : outJ;
+    if (r.x >= 0 && out) out[r.x] = cg_term<KIND>(r.y & 0x7fffff, __hiloint2double(r.w, r.z), cs, o);
   }
 }
 
-__device__ __forceinline__ void cg_all_kinds(const CgTables& t, const CgLists& L, int w, double* __restrict__ out,
-                                             const double* __restrict__ cs, const CgOff& o) {
-  cg_kind_loop<CG_HI>(t, L, w, out, cs, o);
-  cg_kind_loop<CG_CONST>(t, L, w, out, cs, o);
-  cg_kind_loop<CG_PHI2>(t, L, w, out, cs, o);
-  cg_kind_loop<CG_SCR>(t, L, w, out, cs, o);
-  cg_kind_loop<CG_END>(t, L, w, out, cs, o);
-  cg_kind_loop<CG_ENDQ>(t, L, w, out, cs, o);
-  cg_kind_loop<CG_PARTNER>(t, L, w, out, cs, o);
-  cg_kind_loop<CG_SIGH>(t, L, w, out, cs, o);
-  cg_kind_loop<CG_SIGX>(t, L, w, out, cs, o);
-  cg_kind_loop<CG_HHU>(t, L, w, out, cs, o);
-  cg_kind_loop<CG_QHI2>(t, L, w, out, cs, o);
-  cg_kind_loop<CG_HHH>(t, L, w, out, cs, o);
-  cg_kind_loop<CG_HQ>(t, L, w, out, cs, o);
+__device__ __forceinline__ void cg_all_kinds(const CgTables& t, const int4* __restrict__ rec, double* __restrict__ outJ,
+                                             double* __restrict__ outH, const double* __restrict__ cs, const CgOff& o) {
+  cg_kind_loop<CG_HI>(t, rec, outJ, outH, cs, o);
+  cg_kind_loop<CG_CONST>(t, rec, outJ, outH, cs, o);
+  cg_kind_loop<CG_PHI2>(t, rec, outJ, outH, cs, o);
+  cg_kind_loop<CG_SCR>(t, rec, outJ, outH, cs, o);
+  cg_kind_loop<CG_END>(t, rec, outJ, outH, cs, o);
+  cg_kind_loop<CG_ENDQ>(t, rec, outJ, outH, cs, o);
+  cg_kind_loop<CG_PARTNER>(t, rec, outJ, outH, cs, o);
+  cg_kind_loop<CG_SIGH>(t, rec, outJ, outH, cs, o);
+  cg_kind_loop<CG_SIGX>(t, rec, outJ, outH, cs, o);
+  cg_kind_loop<CG_HHU>(t, rec, outJ, outH, cs, o);
+  cg_kind_loop<CG_QHI2>(t, rec, outJ, outH, cs, o);
+  cg_kind_loop<CG_HHH>(t, rec, outJ, outH, cs, o);
+  cg_kind_loop<CG_HQ>(t, rec, outJ, outH, cs, o);
   // entries with several contributions (few)
-  const int nl = t.lptr[w][CG_NKIND];
-  for (int i = threadIdx.x; i < t.nmulti[w]; i += RB_CG_THREADS) {
-    const int slot = L.slot[w][nl + i];
-    if (slot < 0) continue;
+  const int nl = t.lptr[0][CG_NKIND];
+  for (int i = threadIdx.x; i < t.nmulti[0]; i += RB_CG_THREADS) {
+    const int4 r = __ldg(rec + nl + i);
+    double* __restrict__ out = (r.y & 0x800000) ? outH : outJ;
+    if (r.x < 0 || !out) continue;
     double v = 0.0;
-    for (int e = t.mptr[w][i]; e < t.mptr[w][i + 1]; ++e) v += cg_eval(t.mka[w][e], t.mc[w][e], cs, o);
-    out[slot] = v;
+    for (int e = t.mptr[0][i]; e < t.mptr[0][i + 1]; ++e) v += cg_eval(t.mka[0][e], t.mc[0][e], cs, o);
+    out[r.x] = v;
   }
 }
 
@@ -258,12 +256,8 @@ colloc_gather_kernel(const RbDev d, const RbBatch b, const CgTables t, const dou
     }
   }
   CgLists L;
-  L.slot[0] = t.lslot[0] + (size_t)n * t.lstride[0];
-  L.slot[1] = t.lslot[1] + (size_t)n * t.lstride[1];
-  L.arg[0] = t.la[0];
-  L.arg[1] = t.la[1];
-  L.cst[0] = t.lc[0];
-  L.cst[1] = t.lc[1];
+  L.rec[0] = t.rec[0] + (size_t)n * t.lstride[0];
+  L.rec[1] = nullptr;
   const double* __restrict__ C = d.colloc_C;
   const double* __restrict__ D = d.colloc_D;
   const double* __restrict__ Bq = d.colloc_B;
@@ -431,9 +425,9 @@ colloc_gather_kernel(const RbDev d, const RbBatch b, const CgTables t, const dou
       }
     }
     // ---- jac_g, hess_l: every unique entry is produced by one thread ---------------------------------------------------
-    if (b.jac) cg_all_kinds(t, L, 0, b.jac + (size_t)p * d.nnzj, cs, o);
-    __syncthreads();      // SC_ACC (the only Hessian-only scalar) is complete
-    if (b.hess) cg_all_kinds(t, L, 1, b.hess + (size_t)p * d.nnzh, cs, o);
+    __syncthreads();      // SC_ACC (warp 0, needed by the (h, h) Hessian entry) is complete
+    cg_all_kinds(t, L.rec[0], b.jac ? b.jac + (size_t)p * d.nnzj : nullptr, b.hess ? b.hess + (size_t)p * d.nnzh : nullptr,
+                 cs, o);
     __syncthreads();      // the context is free for the next instance
   }
 }

@@ -411,53 +411,69 @@ static int build_gather_tables(rb_problem* p, const rb_problem_desc* s) {
   t.NJ = NJ;
   t.NW = NW;
   t.quat = vi.quat;
-  auto lists = [&](const std::vector<Rec>& rec, const int32_t* tmpl, int nslot, int nuniq, int w, const int32_t* cslot) {
-    std::vector<std::vector<int>> by(nuniq);
-    for (int sidx = 0; sidx < nslot; ++sidx)
-      if (tmpl[sidx] >= 0) {
-        if (tmpl[sidx] >= nuniq || rec[sidx].ka < 0) return 1;
-        by[tmpl[sidx]].push_back(sidx);
-      }
-    std::vector<int32_t> lu, la, mu, mptr(1, 0), mka;
-    std::vector<double> lc, mc;
-    for (int kind = 0; kind < CG_NKIND; ++kind) {
-      t.lptr[w][kind] = (int)lu.size();
-      for (int u = 0; u < nuniq; ++u)
-        if (by[u].size() == 1 && (rec[by[u][0]].ka >> 24) == kind) {
-          lu.push_back(u);
-          la.push_back(rec[by[u][0]].ka);
-          lc.push_back(rec[by[u][0]].c);
-        }
+  // One list for both outputs: per kind the Jacobian entries, then the Hessian entries (flag bit 23 of the argument word)
+  struct Ent { int u, ka, h; double c; };
+  std::vector<std::vector<int>> byJ(s->cell_nj), byH(s->cell_nh);
+  for (int sidx = 0; sidx < NJS; ++sidx)
+    if (s->tmpl_j[sidx] >= 0) {
+      if (s->tmpl_j[sidx] >= s->cell_nj || jr[sidx].ka < 0) return fail("collocation template: entry without a recipe");
+      byJ[s->tmpl_j[sidx]].push_back(sidx);
     }
-    t.lptr[w][CG_NKIND] = (int)lu.size();
-    for (int u = 0; u < nuniq; ++u)
+  for (int sidx = 0; sidx < NHS; ++sidx)
+    if (s->tmpl_h[sidx] >= 0) {
+      if (s->tmpl_h[sidx] >= s->cell_nh || hr[sidx].ka < 0) return fail("collocation template: entry without a recipe");
+      byH[s->tmpl_h[sidx]].push_back(sidx);
+    }
+  std::vector<Ent> single, multi;
+  std::vector<int32_t> mptr(1, 0), mka;
+  std::vector<double> mc;
+  for (int kind = 0; kind < CG_NKIND; ++kind) {
+    t.lptr[0][kind] = (int)single.size();
+    for (int u = 0; u < s->cell_nj; ++u)
+      if (byJ[u].size() == 1 && (jr[byJ[u][0]].ka >> 24) == kind) single.push_back(Ent{u, jr[byJ[u][0]].ka, 0, jr[byJ[u][0]].c});
+    for (int u = 0; u < s->cell_nh; ++u)
+      if (byH[u].size() == 1 && (hr[byH[u][0]].ka >> 24) == kind) single.push_back(Ent{u, hr[byH[u][0]].ka, 1, hr[byH[u][0]].c});
+  }
+  t.lptr[0][CG_NKIND] = (int)single.size();
+  for (int h = 0; h < 2; ++h) {
+    const auto& by = h ? byH : byJ;
+    const auto& rec = h ? hr : jr;
+    for (int u = 0; u < (int)by.size(); ++u)
       if (by[u].size() > 1) {
-        mu.push_back(u);
+        multi.push_back(Ent{u, 0, h, 0.0});
         for (int sidx : by[u]) {
           mka.push_back(rec[sidx].ka);
           mc.push_back(rec[sidx].c);
         }
         mptr.push_back((int32_t)mka.size());
       }
-    t.nmulti[w] = (int)mu.size();
-    t.lstride[w] = (int)(lu.size() + mu.size());
-    std::vector<int32_t> ls((size_t)s->N * t.lstride[w]);
+  }
+  t.nmulti[0] = (int)multi.size();
+  t.lstride[0] = (int)(single.size() + multi.size());
+  for (int k = 0; k <= CG_NKIND; ++k) t.lptr[1][k] = 0;
+  t.nmulti[1] = 0;
+  t.lstride[1] = 0;
+  {
+    std::vector<int4> recs((size_t)s->N * t.lstride[0]);
+    auto slot_of = [&](int n, const Ent& e) {
+      return e.h ? s->cell_hslot[(size_t)n * s->cell_nh + e.u] : s->cell_jslot[(size_t)n * s->cell_nj + e.u];
+    };
     for (int n = 0; n < s->N; ++n) {
-      int32_t* row = ls.data() + (size_t)n * t.lstride[w];
-      for (size_t i = 0; i < lu.size(); ++i) row[i] = cslot[(size_t)n * nuniq + lu[i]];
-      for (size_t i = 0; i < mu.size(); ++i) row[lu.size() + i] = cslot[(size_t)n * nuniq + mu[i]];
+      int4* row = recs.data() + (size_t)n * t.lstride[0];
+      for (size_t i = 0; i < single.size(); ++i) {
+        long long bits;
+        std::memcpy(&bits, &single[i].c, sizeof(bits));
+        row[i] = make_int4(slot_of(n, single[i]), single[i].ka | (single[i].h << 23), (int)(bits & 0xffffffffLL), (int)(bits >> 32));
+      }
+      for (size_t i = 0; i < multi.size(); ++i) row[single.size() + i] = make_int4(slot_of(n, multi[i]), multi[i].h << 23, 0, 0);
     }
     int rc = 0;
-    rc |= upload(p, ls.data(), ls.size(), &t.lslot[w]);
-    rc |= upload(p, la.data(), la.size(), &t.la[w]);
-    rc |= upload(p, lc.data(), lc.size(), &t.lc[w]);
-    rc |= upload(p, mptr.data(), mptr.size(), &t.mptr[w]);
-    rc |= upload(p, mka.data(), mka.size(), &t.mka[w]);
-    rc |= upload(p, mc.data(), mc.size(), &t.mc[w]);
-    return rc;
-  };
-  if (lists(jr, s->tmpl_j, NJS, s->cell_nj, 0, s->cell_jslot)) return fail("collocation template: entry without a recipe");
-  if (lists(hr, s->tmpl_h, NHS, s->cell_nh, 1, s->cell_hslot)) return fail("collocation template: entry without a recipe");
+    rc |= upload(p, recs.data(), recs.size(), &t.rec[0]);
+    rc |= upload(p, mptr.data(), mptr.size(), &t.mptr[0]);
+    rc |= upload(p, mka.data(), mka.size(), &t.mka[0]);
+    rc |= upload(p, mc.data(), mc.size(), &t.mc[0]);
+    if (rc) return 1;
+  }
   p->has_cg = true;
   return 0;
 }
