@@ -69,9 +69,10 @@ def test_kkt_solve_matches_sparse_lu(name, built_library):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('name', ['race_param_rk4_drone', 'fig8_global_colloc_drone', 'obs_param_colloc_drone'])
+@pytest.mark.parametrize('name', ['race_param_rk4_drone', 'fig8_global_colloc_drone', 'obs_param_colloc_drone',
+                                  'fig8cpc_param_colloc_drone'])
 def test_kkt_full_size_residual(name, built_library):
-    ''' full-size C2 (N = 490), C1 (N = 56), C3 (N = 100) structures: residual of the refined solution '''
+    ''' full-size C2 (N = 490), C1 (N = 56), C3 (N = 100), C4 stand-in (N = 200) structures: residual of the refined solution '''
     import torch
     from aircraft_trajectory_optimization_b200.kkt import KktSolver
     prod = build_product(name)
