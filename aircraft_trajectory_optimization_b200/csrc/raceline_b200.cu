@@ -31,6 +31,7 @@
 #include "colloc_cells.cuh"
 #include "colloc_gather.cuh"
 #include "simple_rows.cuh"
+#include "tail_tape.cuh"
 #include "kkt_blocks.cuh"
 #include "kkt_big.cuh"
 #include "kkt_chain.cuh"
@@ -289,6 +290,8 @@ struct rb_problem {
   std::mutex mu;
   CgTables cg{};            // collocation: per-entry recipes of the output-driven kernel (colloc_gather.cuh)
   bool has_cg = false;
+  RbTail tail{};            // open tracks: tape of the end rows (tail_tape.cuh)
+  bool has_tail = false;
 };
 
 namespace {
@@ -624,6 +627,39 @@ int rb_sparsity_get(const rb_problem* p, int which, long long* out) {
   return 0;
 }
 
+int rb_problem_set_tail(rb_problem* p, const rb_tail_desc* s) {
+  if (!p || !s) return fail("rb_problem_set_tail: null argument");
+  if (s->n_ins <= 0 || !s->ins || !s->lvl_ptr || !s->cval || s->n_slots <= 0 || s->n_levels[2] <= 0)
+    return fail("rb_problem_set_tail: empty tape");
+  if (s->n_levels[0] > s->n_levels[1] || s->n_levels[1] > s->n_levels[2] || s->lvl_ptr[s->n_levels[2]] != s->n_ins)
+    return fail("rb_problem_set_tail: inconsistent level table");
+  const size_t smem = (size_t)s->n_slots * sizeof(double);
+  if (smem > 200 * 1024) return fail("rb_problem_set_tail: tape needs more work slots than one CTA's shared memory holds");
+  for (int i = 0; i < s->n_ins; ++i) {
+    const int32_t* q = s->ins + 4 * (size_t)i;
+    const bool store = q[0] >= T_STORE_G;
+    const bool load = q[0] <= T_LOADLAM;
+    bool ok = q[0] >= 0 && q[0] <= T_ADD_H;
+    if (ok && store) ok = q[1] >= 0 && q[1] < s->n_slots && q[2] >= 0 &&
+                          q[2] < (q[0] == T_STORE_G ? p->d.ng : q[0] == T_STORE_J ? p->d.nnzj : p->d.nnzh);
+    if (ok && !store) ok = q[3] >= 0 && q[3] < s->n_slots;
+    if (ok && load) ok = q[1] >= 0 && q[1] < (q[0] == T_CONST ? s->n_const : q[0] == T_LOADX ? p->d.nw : q[0] == T_LOADVP ? p->nvp : p->d.ng);
+    if (ok && !store && !load) ok = q[1] >= 0 && q[1] < s->n_slots && q[2] >= 0 && q[2] < s->n_slots;
+    if (!ok) return fail("rb_problem_set_tail: instruction " + std::to_string(i) + " out of range");
+  }
+  const int32_t* ins = nullptr;
+  int rc = upload(p, s->ins, (size_t)s->n_ins * 4, &ins);
+  rc |= upload(p, s->lvl_ptr, (size_t)s->n_levels[2] + 1, &p->tail.lvl_ptr);
+  rc |= upload(p, s->cval, (size_t)(s->n_const > 0 ? s->n_const : 1), &p->tail.cval);
+  if (rc) return 1;
+  p->tail.ins = reinterpret_cast<const int4*>(ins);
+  p->tail.n_slots = s->n_slots;
+  for (int k = 0; k < 3; ++k) p->tail.n_levels[k] = s->n_levels[k];
+  CK(cudaFuncSetAttribute(tail_tape_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  p->has_tail = true;
+  return 0;
+}
+
 static size_t fpart_bytes(const rb_problem* p, int B) {
   return (((size_t)B * p->d.N * sizeof(double)) + 255) / 256 * 256;
 }
@@ -693,6 +729,12 @@ int rb_eval_batch(const rb_problem* p, int B, const double* x, const double* lam
   if (d.n_shess > 0 && hess) {
     const long long t = (long long)B * d.n_shess;
     simple_hess_kernel<<<(unsigned)((t + 127) / 128), 128, 0, st>>>(d, b);
+    g_launches++;
+    CK(cudaGetLastError());
+  }
+  if (p->has_tail && (g || jac || hess)) {
+    const int nl = p->tail.n_levels[hess ? 2 : jac ? 1 : 0];
+    tail_tape_kernel<<<(unsigned)B, RB_TAIL_THREADS, (size_t)p->tail.n_slots * sizeof(double), st>>>(p->tail, d, b, nl);
     g_launches++;
     CK(cudaGetLastError());
   }

@@ -45,8 +45,14 @@ class _Desc(ctypes.Structure):
     ]
 
 
+class _TailDesc(ctypes.Structure):
+    ''' rb_tail_desc (include/raceline_b200.h): tape of the end rows of an open track '''
+    _fields_ = [('n_ins', ctypes.c_int), ('ins', _c_int_p), ('n_levels', ctypes.c_int * 3), ('lvl_ptr', _c_int_p),
+                ('n_const', ctypes.c_int), ('cval', _c_dbl_p), ('n_slots', ctypes.c_int)]
+
+
 EXPORTS = ['rb_last_error', 'rb_device_count', 'rb_set_device', 'rb_problem_create', 'rb_problem_destroy',
-           'rb_problem_nvp', 'rb_sparsity_size', 'rb_sparsity_get', 'rb_eval_scratch_bytes', 'rb_eval_batch',
+           'rb_problem_nvp', 'rb_problem_set_tail', 'rb_sparsity_size', 'rb_sparsity_get', 'rb_eval_scratch_bytes', 'rb_eval_batch',
            'rb_nlp_f', 'rb_nlp_g', 'rb_nlp_grad_f', 'rb_nlp_jac_g', 'rb_nlp_hess_l', 'rb_nlp_eval_all',
            'rb_launch_count', 'rb_profile_enable', 'rb_profile_cell_ms', 'rb_fp64_peak',
            'rb_kkt_create', 'rb_kkt_set_interiors', 'rb_kkt_destroy', 'rb_kkt_factor_bytes', 'rb_kkt_factor_solve', 'rb_kkt_resolve', 'rb_kkt_resolve_rows',
@@ -76,6 +82,7 @@ def load_library():
     lib.rb_problem_destroy.argtypes = [vp]
     lib.rb_problem_destroy.restype = None
     lib.rb_problem_nvp.argtypes = [vp]
+    lib.rb_problem_set_tail.argtypes = [vp, ctypes.POINTER(_TailDesc)]
     lib.rb_sparsity_size.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_size_t)]
     lib.rb_sparsity_get.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong)]
     lib.rb_eval_scratch_bytes.argtypes = [vp, ctypes.c_int]
@@ -196,6 +203,15 @@ class NlpFunctions:
         _check(self.lib.rb_problem_create(ctypes.byref(self._make_desc()), ctypes.byref(self.handle)),
                'rb_problem_create')
         self.nvp = self.lib.rb_problem_nvp(self.handle)
+        if structure.tail is not None:
+            tp = structure.tail
+            td = _TailDesc()
+            td.n_ins, td.ins = len(tp['ins']), self._arr(tp['ins'], np.int32, _c_int_p)
+            td.n_levels = (ctypes.c_int * 3)(*tp['n_levels'])
+            td.lvl_ptr = self._arr(tp['lvl_ptr'], np.int32, _c_int_p)
+            td.n_const, td.cval = len(tp['cval']), self._arr(tp['cval'], np.float64, _c_dbl_p)
+            td.n_slots = int(tp['n_slots'])
+            _check(self.lib.rb_problem_set_tail(self.handle, ctypes.byref(td)), 'rb_problem_set_tail')
         self.vp = vehicle_params(vehicle_config) if vehicle_config is not None else None
         st = structure
         self.sp_jac = Sparsity(st.ng, st.nw, st.jac_colind, st.jac_row)

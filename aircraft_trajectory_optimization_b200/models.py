@@ -213,6 +213,24 @@ def zdot(variant: Variant, z, u, fc, vp):
     return [*p_dot, *vb_dot]
 
 
+def end_terms(variant: Variant, z, u, vp):
+    '''
+    the helper expressions the open-track end rows use (dynamics_model.py:166-198: ca_f_vg, ca_f_R, ca_f_T), global
+    frame only: dict(vg = global-frame velocity, e3 = third column of the rotation matrix (None for the point mass),
+    Tg = global-frame thrust (point mass: the input itself, point_model.py:28-58)).
+    '''
+    if variant.parametric:
+        raise NotImplementedError('end-row helper expressions of parametric models need the centerline spline '
+                                  'inside the graph (base_centerline.py:117-154); the reference cannot build them either')
+    nr = variant.nr
+    vb = z[3 + nr:6 + nr]
+    if variant.vehicle == 'drone':
+        r = z[3:3 + nr]
+        Rq = _rot_quat(r) if variant.orient == 'quat' else _rot_ypr(r)
+        return dict(vg=_matvec(Rq, vb), e3=[Rq[0][2], Rq[1][2], Rq[2][2]], Tg=None)
+    return dict(vg=list(vb), e3=None, Tg=list(u))
+
+
 # ------------------------------------------------------------------------------------------
 # host-side model objects (reference API: dynamics_model.py:55-250, :253-365)
 # ------------------------------------------------------------------------------------------

@@ -233,8 +233,77 @@ class BaseRaceline:
             if not self.drone:
                 self._enforce_loop_closure()
         else:
-            raise NotImplementedError('open (non-periodic) racelines are not built yet; '
-                                      'all reference scripts use closed tracks')
+            self._enforce_initial_constraints()
+            self._enforce_terminal_constraints()
+
+    # ---- open tracks: expression rows at both ends (tail.py) -----------------------------------
+    def _tail(self):
+        if self.parametric:
+            # the reference's helper functions of parametric models evaluate the centerline spline at the symbolic
+            # path length (base_centerline.py:117-154), which its SX graph cannot hold either
+            raise NotImplementedError('open racelines are built for the global frame only')
+        if self.sb.tail is None:
+            from .tail import TailRows
+            self.sb.tail = TailRows(self.sb, self.model.variant)
+        return self.sb.tail
+
+    def _zF_uF(self):
+        ''' end state and input of the last interval (base_raceline.py:322-348) '''
+        t = self._tail()
+        D = None if self.config.use_rk4 else self.D
+        return t.zF(D), t.uF(D)
+
+    def _end_rows(self, z, u):
+        ''' base_raceline.py:516-543, drone_raceline.py:110-148, point_raceline.py:15-45 '''
+        t = self._tail()
+        tm = t.terms(z, u)
+        vg = tm['vg']
+        t.add_rows([vg[0] * vg[0] + vg[1] * vg[1] + vg[2] * vg[2]], -np.inf, 0.)
+        if self.drone:
+            t.add_rows(tm['e3'], [0., 0., 1.], [0., 0., 1.])
+            t.add_rows(z[-3:], 0., 0.)
+        else:
+            t.add_rows(tm['Tg'][:2], 0., 0.)
+
+    def _enforce_initial_constraints(self):
+        z, u, _ = self._tail().point(0, 0)
+        self._end_rows(z, u)
+
+    def _enforce_terminal_constraints(self):
+        self._end_rows(*self._zF_uF())
+
+    def _fix_gate_expr(self, x, s, include_axial_fix):
+        ''' gate rows for a position given as expressions (the end state zF): base_raceline.py:545-595 '''
+        t = self._tail()
+        t.use()
+        gate_x = self.line.gate_position(s)
+        rc = self.model.config.collision_radius
+        lcfg = self.line.config
+        if self.config.fix_gate_center:
+            t.add_rows([x[i] - float(gate_x[i]) for i in range(3)], 0., 0.)
+            return
+        R = self.line.gate_orientation(s)
+        d = [x[i] - float(gate_x[i]) for i in range(3)]
+
+        def dot(vec, col):
+            acc = 0
+            for i in range(3):
+                acc = acc + vec[i] * float(R[i, col])
+            return acc
+        if lcfg.gate_shape == GateShape.CIRCLE:
+            a, b = dot(d, 1), dot(d, 2)
+            t.add_rows([a * a + b * b], -np.inf, (lcfg.gate_ri - rc) ** 2)
+            if include_axial_fix:
+                t.add_rows([dot(x, 0) - float(gate_x @ R[:, 0])], 0., 0.)
+        elif lcfg.gate_shape == GateShape.SQUARE:
+            d_max = lcfg.gate_ri - rc
+            delta = [dot(d, i) for i in range(3)]
+            if include_axial_fix:
+                t.add_rows(delta, [0., -d_max, -d_max], [0., d_max, d_max])
+            else:
+                t.add_rows(delta[1:], [-d_max, -d_max], [d_max, d_max])
+        else:
+            raise NotImplementedError('Unhandled Gate Shape')
 
     def _stage_constraint(self, n, k):
         ''' point-mass thrust sphere u'u / T_max^2 <= 1 (point_model.py:122-129) '''
@@ -533,6 +602,10 @@ class BaseGlobalRaceline(BaseRaceline):
         for gate_no, n in enumerate(range(0, cfg.N, self.gate_n_interval)):
             vars_ = [sb.iZ(n, 0, i) for i in range(3)]
             self._fix_gate(vars_, np.eye(3), np.eye(3, dtype=bool), np.zeros(3), gate_no, True)
+        if not cfg.closed:
+            # the gate at the very end of an open track sits on the end state (base_raceline.py:914-918)
+            zF, _ = self._zF_uF()
+            self._fix_gate_expr(zF[:3], len(cfg.gate_xi) - 1, True)
 
 
 class BaseParametricRaceline(BaseRaceline):

@@ -50,6 +50,7 @@ class StructureBuilder:
         self.lbg: List[float] = []
         self.ubg: List[float] = []
         self.simple: List[SimpleRow] = []
+        self.tail = None            # tail.TailRows: end rows of open tracks (expression rows, evaluated from a tape)
         if transcription == RK4:
             nr = self.nx
             self.cell_row = -np.ones((N, nr), dtype=np.int32)
@@ -201,6 +202,7 @@ class NLPStructure:
     lbw: np.ndarray = None
     ubw: np.ndarray = None
     w0: np.ndarray = None
+    tail: dict = None       # open tracks: tape of the end rows (tail.py), None otherwise
 
     @property
     def nnz_jac(self):
@@ -249,19 +251,24 @@ def _assemble(sb: StructureBuilder, jent, hent) -> NLPStructure:
     sh_r = np.array([k[0] for k in sh_keys], dtype=np.int64)
     sh_c = np.array([k[1] for k in sh_keys], dtype=np.int64)
 
+    # ---- expression rows of open tracks (tail.py) ---------------------------------------------------
+    z64 = np.zeros(0, dtype=np.int64)
+    (tj_r, tj_c), (th_r, th_c) = sb.tail.entries() if sb.tail is not None else ((z64, z64), (z64, z64))
+
     # ---- jac_g ------------------------------------------------------------------------------------
-    all_r = np.concatenate([jr, sj_r])
-    all_c = np.concatenate([jc, sj_c])
+    all_r = np.concatenate([jr, sj_r, tj_r])
+    all_c = np.concatenate([jc, sj_c, tj_c])
     assert len(np.unique(all_c * ng + all_r)) == len(all_r), 'duplicate Jacobian entry'
     jac_colind, jac_row, jkeys = _ccs(all_r, all_c, ng, nw)
     pos = np.searchsorted(jkeys, all_c * ng + all_r)
     cell_jslot = -np.ones((sb.N, sb.cell_nj), dtype=np.int32)
     cell_jslot[jn, js] = pos[:len(jr)]
-    srow_jslot = pos[len(jr):].astype(np.int32)
+    srow_jslot = pos[len(jr):len(jr) + len(sj_r)].astype(np.int32)
+    tail_jslot = pos[len(jr) + len(sj_r):]
 
     # ---- hess_l -------------------------------------------------------------------------------------
-    all_r = np.concatenate([hr, sh_r])
-    all_c = np.concatenate([hc, sh_c])
+    all_r = np.concatenate([hr, sh_r, th_r])
+    all_c = np.concatenate([hc, sh_c, th_c])
     hess_colind, hess_row, hkeys = _ccs(all_r, all_c, nw, nw)
     assert len(np.unique(hc * nw + hr)) == len(hr), 'cell Hessian blocks overlap'
     hpos = np.searchsorted(hkeys, all_c * nw + all_r)
@@ -269,7 +276,13 @@ def _assemble(sb: StructureBuilder, jent, hent) -> NLPStructure:
     cell_hslot[hn, hs] = hpos[:len(hr)]
     covered = np.zeros(len(hkeys), dtype=bool)
     covered[hpos[:len(hr)]] = True
-    sh_slot = hpos[len(hr):].astype(np.int32)
+    sh_slot = hpos[len(hr):len(hr) + len(sh_r)].astype(np.int32)
+    tail = None
+    if sb.tail is not None:
+        tail_hslot = hpos[len(hr) + len(sh_r):]
+        taken = covered.copy()
+        taken[sh_slot] = True
+        tail = sb.tail.tape(tail_jslot, tail_hslot, taken[tail_hslot])
 
     i32 = lambda v: np.ascontiguousarray(v, dtype=np.int32)
     f64 = lambda v: np.ascontiguousarray(v, dtype=np.float64)
@@ -306,4 +319,4 @@ def _assemble(sb: StructureBuilder, jent, hent) -> NLPStructure:
         transcription=sb.transcription, variant=sb.variant, N=sb.N, K=sb.K, nz=sb.nz, nu=sb.nu,
         nw=nw, ng=ng, R=f64(sb.R), dR=f64(sb.dR), fc=None if sb.fc is None else f64(sb.fc),
         lbg=f64(sb.lbg), ubg=f64(sb.ubg), cell=cell, srow=srow, shess=shess,
-        jac_colind=jac_colind, jac_row=jac_row, hess_colind=hess_colind, hess_row=hess_row)
+        jac_colind=jac_colind, jac_row=jac_row, hess_colind=hess_colind, hess_row=hess_row, tail=tail)

@@ -103,6 +103,24 @@ int rb_problem_create(const rb_problem_desc* desc, rb_problem** out);
 void rb_problem_destroy(rb_problem* p);
 int rb_problem_nvp(const rb_problem* p); /* vehicle parameters per problem instance */
 
+/* ---- end rows of OPEN racelines -------------------------------------------------
+ * `_enforce_initial_constraints` / `_enforce_terminal_constraints` and the gate on the end state
+ * (drone3d/raceline/base_raceline.py:516-543, :914-918, drone_raceline.py:110-148, point_raceline.py:15-45):
+ * a dozen rows that are compositions of the last interval's end state.  CasADi evaluates them as part of the
+ * one SX graph of the NLP; here the host differentiates their expression graph and hands the library a
+ * levelised tape (aircraft_trajectory_optimization_b200/tail.py, csrc/tail_tape.cuh) that every
+ * evaluation runs after the interval kernels.  Optional: closed tracks have no such rows. */
+typedef struct rb_tail_desc {
+  int n_ins;               /* instructions */
+  const int32_t* ins;      /* [n_ins][4] = (op, a, b, dst), opcodes in csrc/tail_tape.cuh */
+  int n_levels[3];         /* levels up to and including the g / Jacobian / Hessian phase */
+  const int32_t* lvl_ptr;  /* [n_levels[2] + 1] first instruction of every level */
+  int n_const;
+  const double* cval;      /* [n_const] constants referenced by T_CONST */
+  int n_slots;             /* work slots (doubles of shared memory per instance) */
+} rb_tail_desc;
+int rb_problem_set_tail(rb_problem* p, const rb_tail_desc* tail);
+
 /* CasADi compressed sparsity of jac_g / hess_l: [nrow, ncol, colind[ncol+1], row[nnz]] as long long.
  * Replaces Function::sparsity_out of nlp_jac_g / nlp_hess_l [CasADi, third party]. */
 int rb_sparsity_size(const rb_problem* p, int which /*0 jac_g, 1 hess_l*/, size_t* n_entries);

@@ -81,7 +81,24 @@ VARIANT_CASES = {
 }
 
 
+# open (non-periodic) racelines, global frame (base_raceline.py:516-543, drone_raceline.py:110-148,
+# point_raceline.py:15-45): initial / terminal rows and the gate on the end state instead of the loop closure
+OPEN_CASES = {
+    'race_global_rk4_point_open': 'race_global_rk4_point',
+    'race_global_rk4_drone_open': 'race_global_rk4_drone',
+    'fig8_global_colloc_point_open': 'fig8_global_colloc_point',
+    'fig8_global_colloc_drone_open': 'fig8_global_colloc_drone',
+    'race_global_rk4_drone_euler_open': 'race_global_rk4_drone',
+}
+
+
+def _closed(name):
+    return name not in OPEN_CASES
+
+
 def _resolve(name, vehicle_kw):
+    if name in OPEN_CASES:
+        name = OPEN_CASES[name]
     if name in VARIANT_CASES:
         base, kw = VARIANT_CASES[name]
         return base, {**kw, **(vehicle_kw or {})}
@@ -97,13 +114,16 @@ def vehicle_config(vehicle, quat=True, tube=False, **kw):
 
 
 def build_product(name, small=False, N=None, vehicle_kw=None):
+    closed = _closed(name)
+    quat_override = False if name.endswith('_euler_open') else None
     name, vehicle_kw = _resolve(name, vehicle_kw)
     track, frame, vehicle, rk4, n_full, n_small, quat, tube = CASES[name]
+    quat = quat if quat_override is None else quat_override
     N = N or (n_small if small else n_full)
     line = make_line(track)
     vc = vehicle_config(vehicle, quat, tube, **(vehicle_kw or {}))
     if frame == 'global':
-        cfg = RL.GlobalRacelineConfig(N=N, use_rk4=rk4, closed=True, verbose=False,
+        cfg = RL.GlobalRacelineConfig(N=N, use_rk4=rk4, closed=closed, verbose=False,
                                       gate_xi=line.config.x[0], gate_xj=line.config.x[1],
                                       gate_xk=line.config.x[2])
         cls = RL.GlobalDroneRaceline if vehicle == 'drone' else RL.GlobalPointRaceline
@@ -132,12 +152,15 @@ def build_product(name, small=False, N=None, vehicle_kw=None):
 def build_oracle(name, small=False, N=None, vehicle_kw=None, ws=None):
     from oracle.ref_centerline import RefSplineCenterline
     from oracle.ref_raceline import RefRaceline, RefTube
+    closed = _closed(name)
+    quat_override = False if name.endswith('_euler_open') else None
     name, vehicle_kw = _resolve(name, vehicle_kw)
     track, frame, vehicle, rk4, n_full, n_small, quat, tube = CASES[name]
+    quat = quat if quat_override is None else quat_override
     N = N or (n_small if small else n_full)
     line = make_line(track, RefSplineCenterline)
     vc = vehicle_config(vehicle, quat, tube, **(vehicle_kw or {}))
-    cfg = NS(N=N, K=7, use_rk4=rk4, R=1e-7, dR=1e-7, h0=1, v0=1, closed=True, fix_gate_center=False)
+    cfg = NS(N=N, K=7, use_rk4=rk4, R=1e-7, dR=1e-7, h0=1, v0=1, closed=closed, fix_gate_center=False)
     rt = None
     if frame == 'global':
         cfg.gate_xi, cfg.gate_xj, cfg.gate_xk = line.config.x

@@ -5,7 +5,7 @@ the same seeded inputs.  fp64; tolerance 1e-10 relative (BASELINE.json north_sta
 import numpy as np
 import pytest
 
-from cases import CASES, VARIANT_CASES, build_case, eval_point
+from cases import CASES, VARIANT_CASES, OPEN_CASES, build_case, eval_point
 
 RTOL = 1e-10
 RK4_CASES = [c for c, v in CASES.items() if v[3]]
@@ -66,6 +66,22 @@ def test_collocation_parity(name, built_library):
 def test_variant_parity(name, built_library):
     ''' frame-relative orientation (global_r=False) and linear-drag variants '''
     _check_case(name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', list(OPEN_CASES))
+def test_open_track_parity(name, built_library):
+    ''' open racelines: initial / terminal rows and the end gate, evaluated from the tape '''
+    _check_case(name)
+    # the g-only and g + Jacobian calls stop the tape early: same values as the all-in-one call
+    prod, _ = build_case(name, small=True)
+    st, F = prod.structure, prod.functions
+    x, lam = eval_point(st, 11)
+    full = F.eval(x, lam_f=1.0, lam_g=lam)
+    assert np.array_equal(F.nlp_g(x, F.vp), full['g'])
+    g2, j2 = F.nlp_jac_g(x, F.vp)
+    assert np.array_equal(g2, full['g']) and np.array_equal(j2, full['jac'])
+    assert np.array_equal(F.nlp_hess_l(x, F.vp, 1.0, lam), full['hess'])
 
 
 @pytest.mark.gpu
