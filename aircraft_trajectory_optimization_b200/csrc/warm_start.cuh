@@ -110,7 +110,9 @@ __global__ void __launch_bounds__(RB_WS_THREADS) ws_point_kernel(const RbWsArgs 
     for (int r = 0; r < 3; ++r) v[r] = -v[r];
     const double s2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2], c = tn[2];
     const double H[9] = {0, -v[2], v[1], v[2], 0, -v[0], -v[1], v[0], 0};
-    const double f = (1.0 - c) / s2;
+    // exactly vertical thrust (the initial / terminal rows of an open point-mass raceline pin T_x = T_y = 0): the
+    // reference's expression is 0 / 0 there; its limit (1 - cos) / sin^2 -> 1/2 gives R = I
+    const double f = s2 > 0.0 ? (1.0 - c) / s2 : 0.5;
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll

@@ -74,6 +74,10 @@ class IpmOptions:
     kappa_w_plus: float = 8.0
     kappa_w_plus_first: float = 100.0
     delta_c_bar: float = 1e-8
+    # a Newton step this much larger than its right-hand side means the KKT matrix is numerically singular although every
+    # pivot passed (a constraint whose gradient vanishes on the feasible set, e.g. the third thrust-axis row of an open
+    # drone raceline, drone_raceline.py:110-148): treated like a vanishing pivot -> delta_c perturbation
+    singular_step_ratio: float = 1e10
     kappa_c: float = 0.25
     refine_steps: int = 4               # at most this many refinement steps per solve; a step is taken only while some
                                        # instance's scaled residual is above refine_tol (IPOPT: residual_ratio_max 1e-10)
@@ -543,6 +547,8 @@ class InteriorPoint:
             for depth in range(len(spec_parts) + 1):
                 finite = torch.isfinite(sol).all(1)
                 singular = (st[:, 0] != 0) | ~finite
+                if rhs.shape == sol.shape:
+                    singular = singular | (sol.abs().amax(1) > o.singular_step_ratio * (1.0 + rhs.abs().amax(1)))
                 wrong_inertia = st[:, 1] != m
                 bad_j = pending & (singular | wrong_inertia)
                 ok_j = pending & ~bad_j

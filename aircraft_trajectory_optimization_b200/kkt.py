@@ -428,8 +428,25 @@ class KktSolver:
         self.lib = load_library()
         bind_kkt(self.lib)
         self.st = st
-        if condensed is None:
+        auto = condensed is None
+        if auto:
             condensed = ks is None and st.K > 0
+        try:
+            self._create(st, ks, condensed)
+        except RuntimeError:
+            if not (auto and condensed):
+                raise
+            # the reduced system of this structure does not fit the shared-memory chain kernels (wide couplings
+            # next to a wide border): the uncondensed global-memory kernel solves it, slower
+            self.__del__()
+            self._create(st, None, False)
+        self._factors = None
+        self._factors_B = 0
+        self._last_B = 0
+
+    def _create(self, st, ks, condensed):
+        _check = self._check
+        self.handle = None
         self.cs = None
         if condensed:
             from .kkt_condensed import build_condensed_structure
@@ -463,9 +480,6 @@ class KktSolver:
                 self._keep.append(a)
                 setattr(di, name, a.ctypes.data_as(_i32p))
             _check(self.lib.rb_kkt_set_interiors(self.handle, ctypes.byref(di)), 'rb_kkt_set_interiors')
-        self._factors = None
-        self._factors_B = 0
-        self._last_B = 0
 
     def __del__(self):
         try:

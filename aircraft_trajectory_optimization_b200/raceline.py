@@ -238,10 +238,6 @@ class BaseRaceline:
 
     # ---- open tracks: expression rows at both ends (tail.py) -----------------------------------
     def _tail(self):
-        if self.parametric:
-            # the reference's helper functions of parametric models evaluate the centerline spline at the symbolic
-            # path length (base_centerline.py:117-154), which its SX graph cannot hold either
-            raise NotImplementedError('open racelines are built for the global frame only')
         if self.sb.tail is None:
             from .tail import TailRows
             self.sb.tail = TailRows(self.sb, self.model.variant)
@@ -266,6 +262,10 @@ class BaseRaceline:
             t.add_rows(tm['Tg'][:2], 0., 0.)
 
     def _enforce_initial_constraints(self):
+        if self.parametric:
+            # the reference's helper functions of parametric models evaluate the centerline spline at the symbolic
+            # path length (base_centerline.py:117-154), which its SX graph cannot hold either
+            raise NotImplementedError('open racelines are built for the global frame only')
         z, u, _ = self._tail().point(0, 0)
         self._end_rows(z, u)
 
@@ -396,13 +396,28 @@ class BaseRaceline:
         ''' point-mass closure: [uF - u0], [zF - z0] (base_raceline.py:492-514, :1183-1227) '''
         sb = self.sb
         nz, nu = self.model.nz, self.model.nu
-        if self.parametric and not self.line.cleanly_closed:
-            raise NotImplementedError('skewly closed centerlines are not built yet')
         rows = sb.alloc_rows(nu, 0., 0.)
         for j, r in enumerate(rows):
             self._end_row(nz + j, r, 1.0, sb.iU(0, 0, j), -1.0, 0.0)
         if self.config.use_rk4:
             sb.cell_par[self.config.N - 1, 0] = 1.0      # uF = U + dU*H  (SURVEY App. D #1)
+        if self.parametric and not self.line.cleanly_closed:
+            # skewly closed centerline (base_raceline.py:1208-1227): the frame at s_max is rotated about the tangent
+            # against the frame at s_min, so the lateral offsets close through a 2x2 rotation.  Those two rows have two
+            # partners each and go through the expression rows (tail.py); the rest are ordinary end rows, sign flipped.
+            line = self.line
+            ey1, en1 = line.p2ey(line.s_min()), line.p2en(line.s_min())
+            ey2, en2 = line.p2ey(line.s_max() - 0.001), line.p2en(line.s_max() - 0.001)
+            A = np.array([[ey1 @ ey2, en1 @ ey2], [ey1 @ en2, en1 @ en2]], dtype=float)
+            t = self._tail()
+            zF, _ = self._zF_uF()
+            z0, _, _ = t.point(0, 0)
+            t.use()
+            t.add_rows([(0 + z0[1] * float(A[i, 0]) + z0[2] * float(A[i, 1])) - zF[1 + i] for i in range(2)], 0., 0.)
+            rows = sb.alloc_rows(nz - 3, 0., 0.)
+            for c, r in zip(range(3, nz), rows):
+                self._end_row(c, r, -1.0, sb.iZ(0, 0, c), 1.0, 0.0)
+            return
         first = 1 if self.parametric else 0
         rows = sb.alloc_rows(nz - first, 0., 0.)
         for c, r in zip(range(first, nz), rows):
@@ -738,7 +753,10 @@ class DroneRaceline(BaseRaceline):
             b = np.array([0, 0, 1])
             tn = T / np.linalg.norm(T)
             v = -np.cross(tn, b)
-            R = np.eye(3) + hat(v) + hat(v) @ hat(v) * (1 - tn @ b) / np.linalg.norm(v) ** 2
+            s2 = float(v @ v)
+            # exactly vertical thrust (the end rows of an open point-mass raceline pin T_x = T_y = 0): 0 / 0 in the
+            # reference's expression (drone_raceline.py:201-204); its limit (1 - cos) / sin^2 -> 1/2 gives R = I
+            R = np.eye(3) + hat(v) + hat(v) @ hat(v) * ((1 - tn @ b) / s2 if s2 > 0 else 0.5)
         if not self.model.config.global_r:
             R = self._guess_Rp(n, k).T @ R
         if quat:

@@ -91,7 +91,9 @@ class TailRows:
             z, u, _ = self.point(n, 0)
             h = self.w(sb.iH(n))
             vp = self.vp()
-            fc = [0.0] * NFC
+            # frame constants of the interval's fixed path length (parametric models: numbers, folded like the
+            # reference's numeric param_terms, base_raceline.py:1034-1048)
+            fc = [0.0] * NFC if sb.fc is None else [float(v) for v in sb.fc[n * sb.P]]
 
             def f(zz):
                 return zdot(self.variant, zz, u, fc, vp)

@@ -40,6 +40,27 @@ def make_line(track, cls=SplineCenterline):
     return line
 
 
+def make_skew_line(track, cls=SplineCenterline, twist=0.6):
+    '''
+    the same waypoints with a provided lateral direction that twists about the tangent along the lap, so that the
+    frame at s_max is rotated against the frame at s_min: a SKEWLY closed centerline (base_raceline.py:1208-1227)
+    '''
+    base = make_line(track)
+    s = np.asarray(base.config.s, dtype=float)
+    ry = []
+    for sk in s:
+        ey, en = base.p2ey(min(sk, base.s_max() - 1e-9)), base.p2en(min(sk, base.s_max() - 1e-9))
+        th = twist * (sk - s[0]) / (s[-1] - s[0])
+        ry.append(np.cos(th) * ey + np.sin(th) * en)
+    x, shape = TRACKS[track]
+    cfg = SplineCenterlineConfig(x=x.copy(), ry=np.array(ry))
+    cfg.closed = True
+    cfg.gate_shape = shape
+    line = cls(cfg)
+    assert not line.cleanly_closed
+    return line
+
+
 def synthetic_tube_arrays(s):
     ''' stand-in tube while trimesh is unavailable '''
     s = np.asarray(s, dtype=float)
@@ -92,6 +113,13 @@ OPEN_CASES = {
 }
 
 
+# skewly closed centerlines (base_raceline.py:1208-1227): parametric point-mass racelines on make_skew_line tracks
+SKEW_CASES = {
+    'race_param_rk4_point_skew': 'race_param_rk4_point',
+    'fig8_param_colloc_point_skew': 'fig8_param_colloc_point',
+}
+
+
 def _closed(name):
     return name not in OPEN_CASES
 
@@ -99,6 +127,8 @@ def _closed(name):
 def _resolve(name, vehicle_kw):
     if name in OPEN_CASES:
         name = OPEN_CASES[name]
+    if name in SKEW_CASES:
+        name = SKEW_CASES[name]
     if name in VARIANT_CASES:
         base, kw = VARIANT_CASES[name]
         return base, {**kw, **(vehicle_kw or {})}
@@ -116,11 +146,12 @@ def vehicle_config(vehicle, quat=True, tube=False, **kw):
 def build_product(name, small=False, N=None, vehicle_kw=None):
     closed = _closed(name)
     quat_override = False if name.endswith('_euler_open') else None
+    skew = name in SKEW_CASES
     name, vehicle_kw = _resolve(name, vehicle_kw)
     track, frame, vehicle, rk4, n_full, n_small, quat, tube = CASES[name]
     quat = quat if quat_override is None else quat_override
     N = N or (n_small if small else n_full)
-    line = make_line(track)
+    line = make_skew_line(track) if skew else make_line(track)
     vc = vehicle_config(vehicle, quat, tube, **(vehicle_kw or {}))
     if frame == 'global':
         cfg = RL.GlobalRacelineConfig(N=N, use_rk4=rk4, closed=closed, verbose=False,
@@ -154,11 +185,12 @@ def build_oracle(name, small=False, N=None, vehicle_kw=None, ws=None):
     from oracle.ref_raceline import RefRaceline, RefTube
     closed = _closed(name)
     quat_override = False if name.endswith('_euler_open') else None
+    skew = name in SKEW_CASES
     name, vehicle_kw = _resolve(name, vehicle_kw)
     track, frame, vehicle, rk4, n_full, n_small, quat, tube = CASES[name]
     quat = quat if quat_override is None else quat_override
     N = N or (n_small if small else n_full)
-    line = make_line(track, RefSplineCenterline)
+    line = make_skew_line(track, RefSplineCenterline) if skew else make_line(track, RefSplineCenterline)
     vc = vehicle_config(vehicle, quat, tube, **(vehicle_kw or {}))
     cfg = NS(N=N, K=7, use_rk4=rk4, R=1e-7, dR=1e-7, h0=1, v0=1, closed=closed, fix_gate_center=False)
     rt = None

@@ -23,7 +23,7 @@ for name, N in [('race_global_rk4_point_open', 7), ('fig8_global_colloc_point_op
     except AssertionError:
         print('   KKT conditions FAILED')
 
-for track, rk4, N in [('race', True, 14), ('fig8', False, 16)]:
+for track, rk4, N in [('race', True, 14), ('fig8', False, 56), ('fig8', False, 16)]:
     line = make_line(track)
     cfg = RL.GlobalRacelineConfig(N=N, use_rk4=rk4, closed=False, verbose=False, gate_xi=line.config.x[0],
                                   gate_xj=line.config.x[1], gate_xk=line.config.x[2])

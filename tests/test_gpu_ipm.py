@@ -35,6 +35,23 @@ def test_point_mass_solve_matches_cpu_golden(name, N, built_library):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize('name,N', [('race_global_rk4_point_open', 7), ('fig8_global_colloc_point_open', 8)])
+def test_open_track_point_mass_solves(name, N, built_library):
+    ''' open racelines: the GPU path converges to the minimum the driver finds on the CPU oracle
+    backend (tests/test_open_tracks.py), a KKT point of the oracle's NLP '''
+    from oracle.nlp_functions import OracleNLP
+    from test_ipm_cpu import _kkt_conditions
+    from test_open_tracks import OPEN_LAPS
+    prod, ref = build_case(name, N=N)
+    res = prod.solve()
+    stats = prod.solver.stats()
+    assert stats['success'] and stats['return_status'] == 'Solve_Succeeded'
+    assert abs(res.time - OPEN_LAPS[(name, N)]) <= LAP_RTOL * res.time
+    _kkt_conditions(prod.structure, OracleNLP(ref, build_hess=False), prod.sol['x'], prod.sol['lam_g'], prod.sol['lam_x'])
+    assert res.feasible and not res.periodic
+
+
+@pytest.mark.gpu
 def test_batched_multistart_solves(built_library):
     ''' B instances in lock step: identical starts give identical answers, perturbed starts still converge '''
     prod = build_product('race_param_rk4_point', N=7)

@@ -5,7 +5,7 @@ the same seeded inputs.  fp64; tolerance 1e-10 relative (BASELINE.json north_sta
 import numpy as np
 import pytest
 
-from cases import CASES, VARIANT_CASES, OPEN_CASES, build_case, eval_point
+from cases import CASES, VARIANT_CASES, OPEN_CASES, SKEW_CASES, build_case, eval_point
 
 RTOL = 1e-10
 RK4_CASES = [c for c, v in CASES.items() if v[3]]
@@ -69,9 +69,10 @@ def test_variant_parity(name, built_library):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('name', list(OPEN_CASES))
+@pytest.mark.parametrize('name', list(OPEN_CASES) + list(SKEW_CASES))
 def test_open_track_parity(name, built_library):
-    ''' open racelines: initial / terminal rows and the end gate, evaluated from the tape '''
+    ''' open racelines and skewly closed centerlines (base_raceline.py:1208-1227): the expression
+    rows -- initial / terminal rows, end gate, skew closure rows -- evaluated from the tape '''
     _check_case(name)
     # the g-only and g + Jacobian calls stop the tape early: same values as the all-in-one call
     prod, _ = build_case(name, small=True)

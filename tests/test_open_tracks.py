@@ -1,17 +1,18 @@
 '''
-Open (non-periodic) racelines, host logic (no GPU): SURVEY.md s8 a8.  The product's builders reproduce the oracle's
+Open (non-periodic) racelines and skewly closed centerlines, host logic (no GPU): SURVEY.md s8 a8 / a7.  The product's builders reproduce the oracle's
 rows, bounds and CCS patterns index for index, and the levelised tape of the end rows (tail.py) -- interpreted here
 with numpy, on the GPU by csrc/tail_tape.cuh -- reproduces the oracle's values of those rows, of their Jacobian
 entries and of the Hessian entries only they touch.  Reference: drone3d/raceline/base_raceline.py:516-543, :914-918,
-drone_raceline.py:110-148, point_raceline.py:15-45.
+drone_raceline.py:110-148, point_raceline.py:15-45; skew closure :1208-1227 (two closure rows with two partners each
+go through the same expression rows).
 '''
 import numpy as np
 import pytest
 
-from cases import OPEN_CASES, build_case, build_product, eval_point
+from cases import OPEN_CASES, SKEW_CASES, build_case, build_product, eval_point
 
 
-@pytest.mark.parametrize('name', list(OPEN_CASES))
+@pytest.mark.parametrize('name', list(OPEN_CASES) + list(SKEW_CASES))
 def test_open_structure_and_tape_match_oracle(name, built_library):
     from oracle.nlp_functions import OracleNLP
     from aircraft_trajectory_optimization_b200.tail import TailRows, T_STORE_G, T_STORE_J, T_STORE_H, T_ADD_H
@@ -75,3 +76,35 @@ def test_open_parametric_raises(built_library):
     cfg = RL.ParametricRacelineConfig(N=7, use_rk4=True, closed=False, verbose=False)
     with pytest.raises(NotImplementedError):
         RL.ParametricPointRaceline(line, cfg, cases.vehicle_config('point'))
+
+
+# lap times of the open point-mass racelines, measured with the interior-point driver on the CPU oracle backend
+# (test_open_point_mass_solve_on_the_cpu_backend below); the GPU solves must reach the same minima
+OPEN_LAPS = {('race_global_rk4_point_open', 7): 5.992371263281883, ('fig8_global_colloc_point_open', 8): 4.803612974951485}
+
+
+def test_open_point_mass_solve_on_the_cpu_backend(built_library):
+    ''' the open NLP is solvable: the driver on the oracle's functions converges to a KKT point of the oracle's NLP '''
+    import torch
+    from oracle.nlp_functions import OracleNLP
+    from oracle.cpu_backend import OracleBackend
+    from aircraft_trajectory_optimization_b200.ipm import InteriorPoint, IpmOptions
+    from aircraft_trajectory_optimization_b200.kkt import build_kkt_structure
+    from test_ipm_cpu import _kkt_conditions
+    name, N = 'race_global_rk4_point_open', 7
+    prod, ref = build_case(name, N=N)
+    st = prod.structure
+    nlp = OracleNLP(ref)
+    be = OracleBackend(nlp, nlp, ks=build_kkt_structure(st))
+    T = lambda a: torch.from_numpy(np.asarray(a, dtype=float))
+    r = InteriorPoint(be, IpmOptions(max_iter=300)).solve(T(st.w0)[None], T(st.lbw), T(st.ubw), T(st.lbg), T(st.ubg))
+    assert r.success.all() and (r.status == 0).all()
+    lap = float(r.x[0, :st.N].sum())
+    assert abs(lap - OPEN_LAPS[(name, N)]) <= 1e-9 * lap
+    x = r.x[0].numpy()
+    _kkt_conditions(st, nlp, x, r.lam_g[0].numpy(), r.lam_x[0].numpy())
+    # the end rows hold: at rest at both ends (vg'vg <= 0 relaxed by the bound relaxation), vertical thrust
+    g = nlp.nlp_g(x)
+    ins = st.tail['ins']
+    rows = ins[ins[:, 0] == 14, 2]
+    assert (g[rows] <= st.ubg[rows] + 1e-7).all() and (g[rows] >= st.lbg[rows] - 1e-7).all()
