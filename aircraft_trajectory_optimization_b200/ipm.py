@@ -77,7 +77,9 @@ class IpmOptions:
     # a Newton step this much larger than its right-hand side means the KKT matrix is numerically singular although every
     # pivot passed (a constraint whose gradient vanishes on the feasible set, e.g. the third thrust-axis row of an open
     # drone raceline, drone_raceline.py:110-148): treated like a vanishing pivot -> delta_c perturbation
-    singular_step_ratio: float = 1e10
+    # Off by default (inf): with 1e10 the hard multi-start instances of the regular problems, whose steps are legitimately
+    # huge for a few iterations, take other paths and some run out of iterations (tests/test_gpu_ipm.py).
+    singular_step_ratio: float = float('inf')
     kappa_c: float = 0.25
     refine_steps: int = 4               # at most this many refinement steps per solve; a step is taken only while some
                                        # instance's scaled residual is above refine_tol (IPOPT: residual_ratio_max 1e-10)
@@ -547,8 +549,8 @@ class InteriorPoint:
             for depth in range(len(spec_parts) + 1):
                 finite = torch.isfinite(sol).all(1)
                 singular = (st[:, 0] != 0) | ~finite
-                if rhs.shape == sol.shape:
-                    singular = singular | (sol.abs().amax(1) > o.singular_step_ratio * (1.0 + rhs.abs().amax(1)))
+                if o.singular_step_ratio < float('inf') and rhs.shape == sol.shape:
+                    singular = singular | (sol.abs().amax(1) > o.singular_step_ratio * torch.clamp(rhs.abs().amax(1), min=1.0))
                 wrong_inertia = st[:, 1] != m
                 bad_j = pending & (singular | wrong_inertia)
                 ok_j = pending & ~bad_j

@@ -244,6 +244,8 @@ class TailRows:
         lvl_ptr = [0]
         for li, items in enumerate(levels):
             dying = set()
+            # same opcodes next to each other: the 32 lanes of a warp then take the same branch of the interpreter
+            items = sorted(items, key=lambda e: (1, e[1]) if e[0] == 's' else (0, op[e[1]]))
             for e in items:
                 if e[0] == 's':
                     _, code, n, dest = e
