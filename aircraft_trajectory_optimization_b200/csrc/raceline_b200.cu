@@ -633,8 +633,7 @@ int rb_problem_set_tail(rb_problem* p, const rb_tail_desc* s) {
     return fail("rb_problem_set_tail: empty tape");
   if (s->n_levels[0] > s->n_levels[1] || s->n_levels[1] > s->n_levels[2] || s->lvl_ptr[s->n_levels[2]] != s->n_ins)
     return fail("rb_problem_set_tail: inconsistent level table");
-  const size_t smem = (size_t)s->n_slots * sizeof(double);
-  if (smem + ((size_t)s->n_levels[2] + 2) * sizeof(int) > 200 * 1024) return fail("rb_problem_set_tail: tape needs more work slots than one CTA's shared memory holds");
+  if (tail_smem_bytes(s->n_slots, s->n_levels[2]) + 16 > 200 * 1024) return fail("rb_problem_set_tail: tape needs more work slots than one CTA's shared memory holds");
   for (int i = 0; i < s->n_ins; ++i) {
     const int32_t* q = s->ins + 4 * (size_t)i;
     const bool store = q[0] >= T_STORE_G;
@@ -734,7 +733,7 @@ int rb_eval_batch(const rb_problem* p, int B, const double* x, const double* lam
   }
   if (p->has_tail && (g || jac || hess)) {
     const int nl = p->tail.n_levels[hess ? 2 : jac ? 1 : 0];
-    tail_tape_kernel<<<(unsigned)B, RB_TAIL_THREADS, (size_t)p->tail.n_slots * sizeof(double) + ((size_t)nl + 2) * sizeof(int), st>>>(p->tail, d, b, nl);
+    tail_tape_kernel<<<(unsigned)B, RB_TAIL_THREADS, tail_smem_bytes(p->tail.n_slots, nl) + 16, st>>>(p->tail, d, b, nl);
     g_launches++;
     CK(cudaGetLastError());
   }

@@ -592,7 +592,7 @@ def main():
     ap.add_argument('--no-colloc', action='store_true', help='skip the C1 (collocation) evaluation leg')
     ap.add_argument('--no-single', action='store_true', help='skip the single-problem solves of the reference scripts')
     ap.add_argument('--solves-batch', type=int, default=2048, help='multi-start instances per GPU in the solves leg')
-    ap.add_argument('--solves-window', type=int, default=888, help='instances iterating at a time (continuous batching)')
+    ap.add_argument('--solves-window', type=int, default=2048, help='instances iterating at a time (continuous batching)')
     ap.add_argument('--solves-refine', type=int, default=4, help='iterative-refinement steps per KKT solve')
     ap.add_argument('--solves-max-iter', type=int, default=300,
                     help='iteration cap per instance in the multi-start sweep (p99 of converged instances is ~280; '
