@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, os.path.dirname(HERE))
 
-from cases import CASES, build_oracle  # noqa: E402
+from cases import CASES, OPEN_CASES, SKEW_CASES, build_oracle, build_product  # noqa: E402
 from oracle.nlp_functions import OracleNLP  # noqa: E402
 
 NSAMPLE = 4000
@@ -36,6 +36,14 @@ def make(name):
                jac_sha=sha(np.concatenate([nlp.jac_colind, nlp.jac_row])),
                hess_sha=sha(np.concatenate([nlp.hess_colind, nlp.hess_row])),
                w0=ref.w0, lbw=ref.lbw, ubw=ref.ubw, lbg=ref.lbg, ubg=ref.ubg)
+    # open racelines / skew closures: EVERY entry the expression rows (tail.py) produce is part of the samples --
+    # they are a few hundred of ~10^5 entries, random samples would hardly meet them
+    extra_j = extra_h = np.zeros(0, dtype=np.int64)
+    if name in OPEN_CASES or name in SKEW_CASES:
+        ins = build_product(name).structure.tail['ins']
+        extra_j = ins[ins[:, 0] == 15, 2].astype(np.int64)
+        extra_h = ins[(ins[:, 0] == 16) | (ins[:, 0] == 17), 2].astype(np.int64)
+        out['tail_rows'] = np.sort(ins[ins[:, 0] == 14, 2].astype(np.int64))
     for seed in (0, 1):
         rng = np.random.default_rng(seed)
         x = np.clip(ref.w0 + 1e-2 * rng.standard_normal(nlp.nw), ref.lbw, ref.ubw)
@@ -45,8 +53,8 @@ def make(name):
         g, jv = nlp.nlp_jac_g(x)
         hv = nlp.nlp_hess_l(x, sigma, lam)
         srng = np.random.default_rng(1000 + seed)
-        ji = np.sort(srng.choice(len(jv), size=min(NSAMPLE, len(jv)), replace=False))
-        hi = np.sort(srng.choice(len(hv), size=min(NSAMPLE, len(hv)), replace=False))
+        ji = np.unique(np.concatenate([srng.choice(len(jv), size=min(NSAMPLE, len(jv)), replace=False), extra_j]))
+        hi = np.unique(np.concatenate([srng.choice(len(hv), size=min(NSAMPLE, len(hv)), replace=False), extra_h]))
         out.update({f'f_{seed}': f, f'grad_f_{seed}': gf, f'g_{seed}': g, f'sigma_{seed}': sigma,
                     f'jac_idx_{seed}': ji, f'jac_val_{seed}': jv[ji], f'jac_sum_{seed}': jv.sum(),
                     f'jac_abs_{seed}': np.abs(jv).sum(),

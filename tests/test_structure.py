@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from cases import CASES, VARIANT_CASES, build_case, build_product
+from cases import CASES, VARIANT_CASES, OPEN_CASES, SKEW_CASES, build_case, build_product
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
@@ -39,7 +39,7 @@ def _sha(a):
     return hashlib.sha256(np.ascontiguousarray(a, dtype=np.int64).tobytes()).hexdigest()
 
 
-@pytest.mark.parametrize('name', list(CASES))
+@pytest.mark.parametrize('name', list(CASES) + list(OPEN_CASES) + list(SKEW_CASES))
 def test_full_size_structure_matches_golden(name, built_library):
     ''' BASELINE.json sizes: patterns (sha256), bounds and initial guess against the oracle fixtures '''
     path = os.path.join(GOLDEN_DIR, f'{name}.npz')
