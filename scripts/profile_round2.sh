@@ -15,3 +15,8 @@ S="python tests/gpu_solves_profile.py 64 64 4"
 $S > gpurun_out/plain_solves.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -s 2000 -c 6000 --csv --log-file gpurun_out/r02_launches_solves.csv $S > gpurun_out/ncu6.log 2>&1
 fi
 ls -la gpurun_out/
+# tail tape kernel (open racelines): bash scripts/profile_round2.sh T
+if [ "$1" = "T" ]; then
+T="python tests/gpu_tail_time.py"
+$T > gpurun_out/plain_tail.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:tail_tape -s 2 -c 1 -o gpurun_out/r02_tail $T > gpurun_out/ncu7.log 2>&1
+fi
