@@ -6,7 +6,7 @@ $E > gpurun_out/plain_eval.log 2>&1 && ncu --metrics gpu__time_duration.sum --cl
 $E > gpurun_out/plain_eval.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:rk4_ -s 20 -c 2 -o gpurun_out/r02_rk4 $E > gpurun_out/ncu2.log 2>&1
 K="python tests/gpu_kkt_bench.py race_param_rk4_drone 444"
 $K > gpurun_out/plain_kkt.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:kkt_factor_kernel\|kkt_solve_kernel -s 2 -c 2 -o gpurun_out/r02_kkt $K > gpurun_out/ncu3.log 2>&1
-else
+elif [ "$1" = "B" ]; then
 K2="python tests/gpu_kkt_bench.py fig8_global_colloc_drone 2"
 $K2 > gpurun_out/plain_kktc.log 2>&1 && ncu --set full --clock-control none -k regex:kktc_ -s 3 -c 3 -o gpurun_out/r02_kktc $K2 > gpurun_out/ncu4.log 2>&1
 C="python tests/gpu_eval_bench.py 256 fig8_global_colloc_drone"
