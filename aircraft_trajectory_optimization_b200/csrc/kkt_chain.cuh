@@ -41,7 +41,9 @@
 // RB_KF_THREADS: warp 0: pivot search; warps 1..5: 4 x 4 tiles of the upper triangle (up to 16 x 16 tiles)
 #define RB_KF_VPAD 72       // update vectors: largest block (64) + tile overhang
 #define RB_KS_THREADS 256
+#ifndef RB_KS_STAGES
 #define RB_KS_STAGES 3
+#endif
 
 struct __align__(16) KfVec {
   double c1[RB_KF_VPAD], r1[RB_KF_VPAD], c2[RB_KF_VPAD], r2[RB_KF_VPAD];
@@ -840,19 +842,37 @@ kkt_solve_kernel(const RbKktDev d, const RbKktChainBatch bt) {
   if (tid == 0)
     for (int s0 = 0; s0 < RB_KS_STAGES && s0 < nsteps; ++s0) issue(s0);
   const int grp = tid >> 3, part = tid & 7;          // eight threads per row of a product
+  // The table entries of a step (block extent, coupling / support extents, border columns, panel offsets) are loaded
+  // one step ahead: a dozen dependent L2 reads per step on the critical path of a 43 x 43 product otherwise.
+  struct Step { int u0, b, cr0, m, sup0, sn, an, po, pq; };
+  auto load_step = [&](int n, bool fwd) {
+    Step t;
+    t.u0 = d.blk_ptr[n];
+    t.b = d.blk_ptr[n + 1] - t.u0;
+    t.cr0 = d.cr_ptr[n];
+    t.m = n < N - 1 ? d.cr_ptr[n + 1] - t.cr0 : 0;
+    t.sup0 = d.sup_ptr[n];
+    t.sn = d.sup_ptr[n + 1] - t.sup0;
+    t.an = d.act[n];
+    t.po = fwd ? d.p_off[n] : d.q_off[n];
+    t.pq = (fwd ? d.p_off[n + 1] : d.q_off[n + 1]) - t.po;
+    return t;
+  };
   int m_prev = 0;
   const int32_t* cr_prev = nullptr;
+  Step nx = load_step(0, true);
   // the right-hand-side entries of the next block are gathered one step ahead (blocks have at most 64 unknowns)
-  double y_next = (tid < d.blk_ptr[1] - d.blk_ptr[0]) ? rhs[d.unk[d.blk_ptr[0] + tid]] : 0.0;
+  double y_next = (tid < nx.b) ? rhs[d.unk[nx.u0 + tid]] : 0.0;
   for (int n = 0; n < N; ++n) {
     const int step = n;
-    const int u0 = d.blk_ptr[n], b = d.blk_ptr[n + 1] - u0;
+    const Step c = nx;
+    const int b = c.b;
+    if (n + 1 < N) nx = load_step(n + 1, true);
     if (tid < b) y[tid] = y_next;
+    // support rows of this block (for the border product below), one per thread
+    const int sup_t = tid < c.sn ? d.sup[c.sup0 + tid] : 0;
     __syncthreads();
-    if (n + 1 < N) {
-      const int u1 = d.blk_ptr[n + 1], b1 = d.blk_ptr[n + 2] - u1;
-      if (tid < b1) y_next = rhs[d.unk[u1 + tid]];
-    }
+    if (n + 1 < N && tid < nx.b) y_next = rhs[d.unk[nx.u0 + tid]];
     if (n > 0) {
       for (int a = tid; a < m_prev; a += blockDim.x) y[cr_prev[a]] -= rc[a];
       __syncthreads();
@@ -875,7 +895,7 @@ kkt_solve_kernel(const RbKktDev d, const RbKktChainBatch bt) {
       }
     }
     if (n < N - 1) {
-      const int m = d.cr_ptr[n + 1] - d.cr_ptr[n];
+      const int m = c.m;
       // L_n S_n^-1 y_n = YL_n' y_n   (S_n is symmetric)
       for (int ab = 0; ab < m; ab += RB_KS_THREADS / 8) {
         const int a = ab + grp;
@@ -888,20 +908,26 @@ kkt_solve_kernel(const RbKktDev d, const RbKktChainBatch bt) {
         if (part == 0 && a < m) rc[a] = acc;
       }
       m_prev = m;
-      cr_prev = d.cr + d.cr_ptr[n];
+      cr_prev = d.cr + c.cr0;
     }
     __syncthreads();                                   // z of this block is complete
+    // z on the support rows, in the place of y (y is rebuilt at the top of the next step)
+    if (tid < c.sn) y[tid] = xn[sup_t];
+    __syncthreads();
     {
-      // r_b -= P_n' z_n[sup]
-      const int sn = d.sup_ptr[n + 1] - d.sup_ptr[n], an = d.act[n];
+      // r_b -= P_n' z_n[sup]: eight threads per border column
+      const int sn = c.sn, an = c.an;
       const int ldq = (an + 1) / 2 * 2;
-      const int pq = d.p_off[n + 1] - d.p_off[n];
-      const double* __restrict__ Pn = (pq <= SZ_PQ) ? Yn + SZ_Y : P_g + d.p_off[n];
-      const int32_t* __restrict__ sup = d.sup + d.sup_ptr[n];
-      for (int j = tid; j < an; j += blockDim.x) {
+      const double* __restrict__ Pn = (c.pq <= SZ_PQ) ? Yn + SZ_Y : P_g + c.po;
+      for (int jb = 0; jb < an; jb += RB_KS_THREADS / 8) {
+        const int j = jb + grp;
         double acc = 0.0;
-        for (int t = 0; t < sn; ++t) acc += Pn[t * ldq + j] * xn[sup[t]];
-        racc[j] += acc;
+        if (j < an)
+          for (int t = part; t < sn; t += 8) acc += Pn[t * ldq + j] * y[t];
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if (part == 0 && j < an) racc[j] += acc;
       }
     }
     __syncthreads();                                   // this buffer, y and xn are free again
@@ -921,23 +947,25 @@ kkt_solve_kernel(const RbKktDev d, const RbKktChainBatch bt) {
     __syncthreads();
   }
   // ---- backward: x_n = z_n - Q_n x_b - YL_n x_{n+1}[cr]
-  double z_next = (tid < d.blk_ptr[N] - d.blk_ptr[N - 1]) ? Xr[(size_t)(N - 1) * bmax + tid] : 0.0;
+  nx = load_step(N - 1, false);
+  double z_next = (tid < nx.b) ? Xr[(size_t)(N - 1) * bmax + tid] : 0.0;
   for (int n = N - 1; n >= 0; --n) {
     const int step = 2 * N - 1 - n;
-    const int u0 = d.blk_ptr[n], b = d.blk_ptr[n + 1] - u0;
+    const Step c = nx;
+    const int u0 = c.u0, b = c.b;
+    if (n > 0) nx = load_step(n - 1, false);
     const double z_cur = z_next;
-    if (n > 0 && tid < d.blk_ptr[n] - d.blk_ptr[n - 1]) z_next = Xr[(size_t)(n - 1) * bmax + tid];
-    const int m = n < N - 1 ? d.cr_ptr[n + 1] - d.cr_ptr[n] : 0;
-    const int32_t* __restrict__ cr = d.cr + d.cr_ptr[n];
+    const int m = c.m;
+    const int32_t* __restrict__ cr = d.cr + c.cr0;
     for (int a = tid; a < m; a += blockDim.x) rc[a] = xn[cr[a]];
     if (tid < b) y[tid] = z_cur;
     wait(step);
     __syncthreads();
+    if (n > 0 && tid < nx.b) z_next = Xr[(size_t)(n - 1) * bmax + tid];
     const double* __restrict__ Yn = buf0 + (size_t)(step % RB_KS_STAGES) * BUF + SZ_S;
-    const int an = d.act[n];
+    const int an = c.an;
     const int ldq = (an + 1) / 2 * 2;
-    const int qq = d.q_off[n + 1] - d.q_off[n];
-    const double* __restrict__ Qn = (qq <= SZ_S) ? Yn - SZ_S : Q_g + d.q_off[n];
+    const double* __restrict__ Qn = (c.pq <= SZ_S) ? Yn - SZ_S : Q_g + c.po;
     for (int ib = 0; ib < b; ib += RB_KS_THREADS / 8) {
       const int i = ib + grp;
       double acc = 0.0;

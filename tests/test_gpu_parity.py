@@ -86,10 +86,12 @@ def test_open_track_parity(name, built_library):
 
 
 @pytest.mark.gpu
-def test_batch_matches_single(built_library):
-    ''' a batch of B instances with per-instance vehicle parameters == B single calls '''
+@pytest.mark.parametrize('name', ['race_param_rk4_drone', 'race_global_rk4_drone_open', 'fig8_global_colloc_point_open'])
+def test_batch_matches_single(name, built_library):
+    ''' a batch of B instances with per-instance vehicle parameters == B single calls (open racelines: the tape
+    kernel runs one CTA per instance and reads the instance's own vehicle parameters) '''
     from aircraft_trajectory_optimization_b200.models import vehicle_params
-    prod, _ = build_case('race_param_rk4_drone', small=True)
+    prod, _ = build_case(name, small=True)
     st, F = prod.structure, prod.functions
     B = 5
     rng = np.random.default_rng(3)
