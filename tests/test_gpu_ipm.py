@@ -155,10 +155,14 @@ def test_fused_sweep_kernels_match_the_torch_arithmetic(name, built_library):
     for key in ('glue', 'glue_compact'):
         conv_k = out[key][1] <= 1
         assert conv_k.sum() >= B - 1, (key, out[key][1])
-        # instances that converge quickly follow the same path to rounding
-        same = (np.abs(out[key][2] - out['torch'][2]) <= 2) & conv_t & conv_k
+        # instances that converge quickly follow the same path to rounding; the perturbed starts may end in another of
+        # the track's local minima (laps 5.797 .. 5.820 s) when a path forks: compared are the instances that reach the
+        # same minimum in about the same number of iterations
+        laps_t = out['torch'][0]['x'][:, :st.N].sum(1)
+        laps_k = out[key][0]['x'][:, :st.N].sum(1)
+        same = (np.abs(out[key][2] - out['torch'][2]) <= 2) & conv_t & conv_k & (np.abs(laps_k - laps_t) <= 1e-6)
         assert np.array_equal(out[key][1][same], out['torch'][1][same]), key
-        assert same.sum() >= B // 2, (key, out[key][2], out['torch'][2])
+        assert same[0] and same.sum() >= B // 2, (key, out[key][2], out['torch'][2])
         for k in ('x', 'lam_g'):
             scale = max(1.0, np.abs(out['torch'][0][k]).max())
             assert np.abs(out[key][0][k][same] - out['torch'][0][k][same]).max() <= 1e-6 * scale, (key, k)
