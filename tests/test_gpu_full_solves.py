@@ -7,6 +7,7 @@ restatement of the reference's warm-start mapping, drone3d/raceline/drone_raceli
 
   C2: scripts/race.py:42-49   parametric quaternion drone, RK4, N = 490 (solve_util N = 70 x 7 gates)
   C1: scripts/fig_8.py:55-62  global-frame quaternion drone, Legendre collocation N = 56, K = 7
+  C3: scripts/obstacles.py:14-44  parametric quaternion drone inside the (synthetic) obstacle-free tube, N = 100, K = 7
 
 The reference's own golden for these numbers would be an IPOPT run (CasADi is not in the image: parity unpinned).
 '''
@@ -17,15 +18,33 @@ from cases import CASES, build_oracle, make_line
 from test_ipm_cpu import _kkt_conditions
 
 
+def _solve_obstacles():
+    ''' scripts/obstacles.py:14-44 with the synthetic tube of SURVEY.md s8d (C3) '''
+    from cases import synthetic_tube_arrays, vehicle_config
+    from aircraft_trajectory_optimization_b200 import raceline as RL
+    line = make_line('obs')
+    cfg = RL.ParametricRacelineConfig(N=100, use_rk4=False, closed=True, verbose=False)
+    vc = vehicle_config('drone', True, True)
+    tau = RL.get_collocation_coefficients(cfg.K)[0]
+    ds = (line.s_max() - line.s_min()) / cfg.N
+    s_all = np.array([line.s_min() + ds * (n + tau[k]) for n in range(cfg.N) for k in range(cfg.K + 1)])
+    tube = RL.ObstacleFreeTube(*synthetic_tube_arrays(s_all), vc.collision_radius)
+    solver = RL.ParametricObstacleDroneRaceline(line, cfg, vc, None, tube, generate_ws=True)
+    return solver, solver.solve()
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize('name', ['race_param_rk4_drone', 'fig8_global_colloc_drone'])
+@pytest.mark.parametrize('name', ['race_param_rk4_drone', 'fig8_global_colloc_drone', 'obs_param_colloc_drone'])
 def test_full_size_drone_solve_is_a_kkt_point_of_the_oracle_nlp(name, built_library):
     from oracle.nlp_functions import OracleNLP
     from aircraft_trajectory_optimization_b200.solve_util import solve_util
-    track, frame, vehicle, rk4, n_full, _, quat, _ = CASES[name]
+    track, frame, vehicle, rk4, n_full, _, quat, tube = CASES[name]
     line = make_line(track)
-    solver, res = solve_util(line, global_frame=(frame == 'global'), drone=True, use_quaternion=quat, use_ws=True,
-                             use_rk4=rk4, N=n_full, verbose=False)
+    if tube:
+        solver, res = _solve_obstacles()
+    else:
+        solver, res = solve_util(line, global_frame=(frame == 'global'), drone=True, use_quaternion=quat, use_ws=True,
+                                 use_rk4=rk4, N=n_full, verbose=False)
     st = solver.structure
     stats = solver.solver.stats()
     assert stats['success'], stats['return_status']
