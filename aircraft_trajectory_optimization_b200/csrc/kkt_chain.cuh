@@ -859,7 +859,7 @@ kkt_solve_kernel(const RbKktDev d, const RbKktChainBatch bt) {
     return t;
   };
   int m_prev = 0;
-  const int32_t* cr_prev = nullptr;
+  int cr_prev_t = 0;        // this thread's coupling row of the previous block (its carry entry lands there)
   Step nx = load_step(0, true);
   // the right-hand-side entries of the next block are gathered one step ahead (blocks have at most 64 unknowns)
   double y_next = (tid < nx.b) ? rhs[d.unk[nx.u0 + tid]] : 0.0;
@@ -869,12 +869,14 @@ kkt_solve_kernel(const RbKktDev d, const RbKktChainBatch bt) {
     const int b = c.b;
     if (n + 1 < N) nx = load_step(n + 1, true);
     if (tid < b) y[tid] = y_next;
-    // support rows of this block (for the border product below), one per thread
+    // support rows of this block (for the border product below) and its coupling rows (for the carry of the next
+    // step), one per thread: index loads off the critical path
     const int sup_t = tid < c.sn ? d.sup[c.sup0 + tid] : 0;
+    const int cr_t = tid < c.m ? d.cr[c.cr0 + tid] : 0;
     __syncthreads();
     if (n + 1 < N && tid < nx.b) y_next = rhs[d.unk[nx.u0 + tid]];
     if (n > 0) {
-      for (int a = tid; a < m_prev; a += blockDim.x) y[cr_prev[a]] -= rc[a];
+      if (tid < m_prev) y[cr_prev_t] -= rc[tid];
       __syncthreads();
     }
     wait(step);
@@ -908,7 +910,7 @@ kkt_solve_kernel(const RbKktDev d, const RbKktChainBatch bt) {
         if (part == 0 && a < m) rc[a] = acc;
       }
       m_prev = m;
-      cr_prev = d.cr + c.cr0;
+      cr_prev_t = cr_t;
     }
     __syncthreads();                                   // z of this block is complete
     // z on the support rows, in the place of y (y is rebuilt at the top of the next step)
@@ -949,15 +951,21 @@ kkt_solve_kernel(const RbKktDev d, const RbKktChainBatch bt) {
   // ---- backward: x_n = z_n - Q_n x_b - YL_n x_{n+1}[cr]
   nx = load_step(N - 1, false);
   double z_next = (tid < nx.b) ? Xr[(size_t)(N - 1) * bmax + tid] : 0.0;
+  int cr_nx = tid < nx.m ? d.cr[nx.cr0 + tid] : 0;         // coupling row / unknown index of the next step, per thread
+  int unk_nx = tid < nx.b ? d.unk[nx.u0 + tid] : 0;
   for (int n = N - 1; n >= 0; --n) {
     const int step = 2 * N - 1 - n;
     const Step c = nx;
-    const int u0 = c.u0, b = c.b;
-    if (n > 0) nx = load_step(n - 1, false);
+    const int b = c.b;
+    const int cr_t = cr_nx, unk_t = unk_nx;
+    if (n > 0) {
+      nx = load_step(n - 1, false);
+      cr_nx = tid < nx.m ? d.cr[nx.cr0 + tid] : 0;
+      unk_nx = tid < nx.b ? d.unk[nx.u0 + tid] : 0;
+    }
     const double z_cur = z_next;
     const int m = c.m;
-    const int32_t* __restrict__ cr = d.cr + c.cr0;
-    for (int a = tid; a < m; a += blockDim.x) rc[a] = xn[cr[a]];
+    if (tid < m) rc[tid] = xn[cr_t];
     if (tid < b) y[tid] = z_cur;
     wait(step);
     __syncthreads();
@@ -982,7 +990,7 @@ kkt_solve_kernel(const RbKktDev d, const RbKktChainBatch bt) {
     if (tid < b) {
       const double xv = y[tid];
       xn[tid] = xv;
-      sol[d.unk[u0 + tid]] = xv;
+      sol[unk_t] = xv;
     }
     if (tid == 0 && step + RB_KS_STAGES < nsteps) issue(step + RB_KS_STAGES);
     __syncthreads();
