@@ -42,6 +42,32 @@ def test_unknown_variant_is_refused(built_library):
 
 
 @pytest.mark.gpu
+def test_malformed_tail_tape_is_refused(built_library):
+    ''' rb_problem_set_tail checks every instruction against the problem's sizes before anything reaches the device '''
+    from aircraft_trajectory_optimization_b200.functions import NlpFunctions
+    prod = build_product('race_global_rk4_point_open', small=True)
+    st = prod.structure
+    for col, bad_value, what in ((3, st.tail['n_slots'], 'out of range'),       # destination slot beyond the work array
+                                 (0, 99, 'out of range')):                      # unknown opcode
+        tape = {**st.tail, 'ins': st.tail['ins'].copy()}
+        tape['ins'][5, col] = bad_value
+        bad = type(st)(**{**st.__dict__, 'tail': tape})
+        with pytest.raises(RuntimeError, match=what):
+            NlpFunctions(bad, prod.vehicle_config)
+    # a store beyond the Jacobian values
+    tape = {**st.tail, 'ins': st.tail['ins'].copy()}
+    k = int(np.nonzero(tape['ins'][:, 0] == 15)[0][0])
+    tape['ins'][k, 2] = st.nnz_jac
+    with pytest.raises(RuntimeError, match='out of range'):
+        NlpFunctions(type(st)(**{**st.__dict__, 'tail': tape}), prod.vehicle_config)
+    # level table that does not end at the last instruction
+    tape = {**st.tail, 'lvl_ptr': st.tail['lvl_ptr'].copy()}
+    tape['lvl_ptr'][-1] -= 1
+    with pytest.raises(RuntimeError, match='level table'):
+        NlpFunctions(type(st)(**{**st.__dict__, 'tail': tape}), prod.vehicle_config)
+
+
+@pytest.mark.gpu
 def test_per_instance_frame_constants_match_shared(built_library):
     ''' track sweeps pass frame constants per instance (fc_b); equal tables must reproduce the shared result '''
     import torch
