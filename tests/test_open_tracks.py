@@ -9,7 +9,7 @@ go through the same expression rows).
 import numpy as np
 import pytest
 
-from cases import OPEN_CASES, SKEW_CASES, build_case, build_product, eval_point
+from cases import OPEN_CASES, SKEW_CASES, build_case, eval_point
 
 
 @pytest.mark.parametrize('name', list(OPEN_CASES) + list(SKEW_CASES))
