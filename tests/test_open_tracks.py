@@ -108,3 +108,36 @@ def test_open_point_mass_solve_on_the_cpu_backend(built_library):
     ins = st.tail['ins']
     rows = ins[ins[:, 0] == 14, 2]
     assert (g[rows] <= st.ubg[rows] + 1e-7).all() and (g[rows] >= st.lbg[rows] - 1e-7).all()
+
+
+@pytest.mark.parametrize('name', ['race_global_rk4_point_open', 'race_global_rk4_drone_open', 'fig8_global_colloc_point_open',
+                                  'race_param_rk4_point_skew'])
+def test_open_kkt_block_tables_reproduce_the_sparse_solve(name, built_library):
+    '''
+    the KKT block analysis (kkt.py) needs no special case for open tracks: x_0 and the end rows join the border, the
+    chain is walked by the numpy twin of csrc/kkt_chain.cuh and compared with SuperLU and a dense eigendecomposition.
+    The end rows of open DRONE racelines are rank deficient by construction (R(qF)[:,2] = e3 on the renormalised
+    quaternion: the gradient of the third row vanishes on the feasible set), so the equality rows carry the
+    delta_c > 0 the interior-point driver gives them in that case.
+    '''
+    from oracle.nlp_functions import OracleNLP
+    from oracle.kkt_blocks_ref import kkt_matrix, sparse_solve, chain_factor, chain_solve
+    from aircraft_trajectory_optimization_b200.kkt import build_kkt_structure
+    from test_kkt_structure import _kkt_inputs
+    prod, ref = build_case(name, small=True)
+    st = prod.structure
+    ks = build_kkt_structure(st)
+    assert np.array_equal(np.sort(ks.unk), np.arange(st.nw + st.ng))
+    assert ks.bmax <= 64 or st.K > 0
+    nlp = OracleNLP(ref)
+    hess, jac, dxd, D, rhs = _kkt_inputs(st, nlp, 0)
+    D = np.maximum(D, 1e-5)
+    K = kkt_matrix(st, hess, jac, dxd, D)
+    ref_sol = sparse_solve(st, hess, jac, dxd, D, rhs)
+    F, neg = chain_factor(ks, hess, jac, dxd, D)
+    sol = chain_solve(ks, F, rhs)
+    for _ in range(2):
+        sol = sol + chain_solve(ks, F, rhs - K @ sol)
+    assert np.abs(K @ sol - rhs).max() <= 1e-9 * max(1.0, np.abs(rhs).max())
+    assert np.abs(sol - ref_sol).max() <= 1e-7 * np.abs(ref_sol).max()
+    assert neg == int((np.linalg.eigvalsh(K.toarray()) < 0).sum())
