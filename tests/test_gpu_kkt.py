@@ -12,7 +12,10 @@ RK4_CASES = [c for c, v in CASES.items() if v[3]]
 # collocation structures: interiors condensed (csrc/kkt_condense.cuh) + chain kernels on the reduced system; the
 # uncondensed large-block kernel (csrc/kkt_big.cuh) is kept and tested on one structure ('@big')
 KKT_CASES = RK4_CASES + ['fig8_global_colloc_point', 'fig8_global_colloc_drone', 'fig8_param_colloc_drone',
-                         'fig8_param_colloc_drone_euler', 'obs_param_colloc_point', 'fig8_global_colloc_point@big']
+                         'fig8_param_colloc_drone_euler', 'obs_param_colloc_point', 'fig8_global_colloc_point@big',
+                         # open racelines / skew closure (point mass: the end rows of open drone racelines are rank
+                         # deficient by construction, tests/test_open_tracks.py)
+                         'race_global_rk4_point_open', 'fig8_global_colloc_point_open', 'race_param_rk4_point_skew']
 
 
 def _inputs(st, F, B, seed=0):
