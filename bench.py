@@ -586,7 +586,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=2048, help='problem instances per GPU per step')
-    ap.add_argument('--e2e-batch', type=int, default=256)
+    ap.add_argument('--e2e-batch', type=int, default=1024)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-solves', action='store_true', help='skip the converged-solves leg')
     ap.add_argument('--no-colloc', action='store_true', help='skip the C1 (collocation) evaluation leg')
